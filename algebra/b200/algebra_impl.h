@@ -1,0 +1,51 @@
+/*
+ * algebra/b200 -- definitions of OSQP's opaque algebra types for the B200 backend.
+ *
+ * Counterpart of /root/reference/algebra/cuda/algebra_types.h:31-59 and
+ * algebra/builtin/algebra_impl.h:16-45.  All numerical data lives in B200 HBM and is only
+ * touched through the C-ABI in include/osqp_b200.h.
+ */
+#ifndef ALGEBRA_IMPL_H
+#define ALGEBRA_IMPL_H
+
+#include "osqp_api_types.h"
+#include "osqp_b200.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+struct OSQPVectori_ {
+  OSQPInt* d_val;     /* device array */
+  OSQPInt  length;
+};
+
+struct OSQPVectorf_ {
+  OSQPFloat* d_val;   /* device array (b200_float == OSQPFloat) */
+  OSQPInt    length;
+  OSQPInt    is_view; /* 1: d_val aliases a parent vector and is not freed */
+};
+
+/*
+ * A (m x n) is kept twice, as CSR of A and as CSR of A' (== the user's CSC arrays, so the
+ * transpose costs nothing and A'x never needs atomics).  P (symmetric) is expanded from the
+ * user's upper triangle to a full CSR with a structurally full diagonal.
+ * The host maps translate positions in the USER's CSC value array into positions of the
+ * device value arrays for OSQPMatrix_update_values (reference: d_A_to_At_ind /
+ * d_P_triu_to_full_ind, algebra/cuda/algebra_types.h:51-59).
+ */
+struct OSQPMatrix_ {
+  b200_csr* S;        /* CSR of the matrix itself (A, or full symmetric P)      */
+  b200_csr* St;       /* CSR of A'; NULL for symmetric P                         */
+  OSQPInt   m, n;     /* rows, columns                                           */
+  OSQPInt   nnz_user; /* entries in the user's CSC (triu count for P)            */
+  OSQPInt   is_symmetric;
+  OSQPInt*  h_map;    /* user CSC k -> position in S (A: CSR pos; P: upper copy) */
+  OSQPInt*  h_map2;   /* P only: position of the mirrored copy, -1 on diagonal   */
+};
+
+#ifdef __cplusplus
+}
+#endif
+
+#endif /* ALGEBRA_IMPL_H */

@@ -1,0 +1,38 @@
+/*
+ * algebra/b200/b200_extras.c -- small exported helpers that need the private workspace
+ * layout (include/private/types.h).  Not part of OSQP's interface; used by the Python host
+ * mirror, bench.py and the tests for metrics the reference does not expose.
+ */
+#include "osqp.h"
+#include "types.h"
+#include "pcg_interface.h"
+
+/* total CG iterations and number of linear solves of this solver (synchronises) */
+OSQPInt osqp_b200_cg_stats(const OSQPSolver* solver, long long* total_iters, long long* n_solves) {
+  if (!solver || !solver->work || !solver->work->linsys_solver) return 1;
+  b200pcg_get_stats(solver->work->linsys_solver, total_iters, n_solves);
+  return 0;
+}
+
+/* problem sizes as stored by the backend: n, m, nnz(A), nnz(P triu) */
+OSQPInt osqp_b200_dims(const OSQPSolver* solver, OSQPInt* n, OSQPInt* m, OSQPInt* nnzA,
+                       OSQPInt* nnzP) {
+  if (!solver || !solver->work || !solver->work->data) return 1;
+  *n    = solver->work->data->n;
+  *m    = solver->work->data->m;
+  *nnzA = OSQPMatrix_get_nz(solver->work->data->A);
+  *nnzP = OSQPMatrix_get_nz(solver->work->data->P);
+  return 0;
+}
+
+/* sizes of the public structs this library was compiled with (ctypes layout check) */
+OSQPInt osqp_b200_sizeof(OSQPInt which) {
+  switch (which) {
+  case 0: return (OSQPInt)sizeof(OSQPSettings);
+  case 1: return (OSQPInt)sizeof(OSQPInfo);
+  case 2: return (OSQPInt)sizeof(OSQPCscMatrix);
+  case 3: return (OSQPInt)sizeof(OSQPFloat);
+  case 4: return (OSQPInt)sizeof(OSQPInt);
+  default: return -1;
+  }
+}

@@ -1,0 +1,348 @@
+/*
+ * algebra/b200/matrix.c -- OSQPMatrix over B200 device CSR storage.
+ *
+ * Implements /root/reference/include/private/algebra_matrix.h:26-138.  Numerical contract =
+ * CPU reference (algebra/builtin/matrix.c, algebra/_common/csc_math.c); storage design takes
+ * over the role of algebra/cuda/matrix.cu:32-172 + src/cuda_csr.cu:489-714 (CSR of A, stored
+ * transpose, full symmetric P with guaranteed diagonal, index maps for value updates) but the
+ * format conversions are plain counting sorts on the host instead of cuSPARSE/thrust calls:
+ *   - the user's CSC of A *is* the CSR of A' -> no work, identity value map;
+ *   - CSR of A = one counting sort by row, recording where every CSC entry lands;
+ *   - full P = lower mirror + upper copy of the triu CSC, diagonal inserted where missing.
+ */
+#include "osqp.h"
+#include "algebra_matrix.h"
+#include "algebra_impl.h"
+#include "glob_opts.h"
+#include "printing.h"
+
+#include <string.h>
+
+/* ------------------------------------------------------------------ builders */
+
+/* CSR of an m x n matrix from its CSC arrays; map[k] = CSR position of CSC entry k */
+static b200_csr* csr_from_csc(OSQPInt m, OSQPInt n, const OSQPInt* Ap, const OSQPInt* Ai,
+                              const OSQPFloat* Ax, OSQPInt* map) {
+  OSQPInt   nnz = Ap[n];
+  OSQPInt   i, j, k, pos;
+  b200_csr* out = OSQP_NULL;
+  OSQPInt*   rp   = (OSQPInt*)c_calloc((size_t)m + 2, sizeof(OSQPInt));
+  OSQPInt*   next = (OSQPInt*)c_malloc(((size_t)m + 1) * sizeof(OSQPInt));
+  OSQPInt*   ci   = (OSQPInt*)c_malloc(((size_t)nnz + 1) * sizeof(OSQPInt));
+  OSQPFloat* vx   = (OSQPFloat*)c_malloc(((size_t)nnz + 1) * sizeof(OSQPFloat));
+
+  if (rp && next && ci && vx) {
+    for (k = 0; k < nnz; k++) rp[Ai[k] + 1]++;
+    for (i = 0; i < m; i++) rp[i + 1] += rp[i];
+    for (i = 0; i < m; i++) next[i] = rp[i];
+    for (j = 0; j < n; j++) {
+      for (k = Ap[j]; k < Ap[j + 1]; k++) {
+        pos     = next[Ai[k]]++;
+        ci[pos] = j;
+        vx[pos] = Ax[k];
+        if (map) map[k] = pos;
+      }
+    }
+    out = b200_csr_create((int)m, (int)n, (int)nnz, rp, ci, vx);
+  }
+  c_free(rp); c_free(next); c_free(ci); c_free(vx);
+  return out;
+}
+
+/* full symmetric CSR (structurally full diagonal) from an upper-triangular CSC.
+ * map_u[k]: position of entry k itself (row i, col j); map_l[k]: position of its mirror
+ * (row j, col i) or -1 for diagonal entries.  Rows come out with sorted columns when the
+ * CSC columns are sorted. */
+static b200_csr* full_from_triu(OSQPInt n, const OSQPInt* Pp, const OSQPInt* Pi,
+                                const OSQPFloat* Px, OSQPInt* map_u, OSQPInt* map_l) {
+  OSQPInt   nnz = Pp[n];
+  OSQPInt   i, j, k, pos, nnz_full;
+  b200_csr* out = OSQP_NULL;
+  OSQPInt* rp       = (OSQPInt*)c_calloc((size_t)n + 2, sizeof(OSQPInt));
+  OSQPInt* next     = (OSQPInt*)c_malloc(((size_t)n + 1) * sizeof(OSQPInt));
+  char*    has_diag = (char*)c_calloc((size_t)n + 1, 1);
+  OSQPInt*   ci = OSQP_NULL;
+  OSQPFloat* vx = OSQP_NULL;
+
+  if (!rp || !next || !has_diag) goto done;
+
+  for (j = 0; j < n; j++) {
+    for (k = Pp[j]; k < Pp[j + 1]; k++) {
+      i = Pi[k];
+      rp[i + 1]++;                       /* (i, j) */
+      if (i != j) rp[j + 1]++;           /* mirror (j, i) */
+      else has_diag[j] = 1;
+    }
+  }
+  for (i = 0; i < n; i++) {
+    if (!has_diag[i]) rp[i + 1]++;       /* explicit zero on the diagonal */
+    rp[i + 1] += rp[i];
+  }
+  nnz_full = rp[n];
+  ci = (OSQPInt*)c_malloc(((size_t)nnz_full + 1) * sizeof(OSQPInt));
+  vx = (OSQPFloat*)c_malloc(((size_t)nnz_full + 1) * sizeof(OSQPFloat));
+  if (!ci || !vx) goto done;
+  for (i = 0; i < n; i++) next[i] = rp[i];
+
+  /* pass 1: strictly-lower mirrors, row j receives columns i < j in CSC order */
+  for (j = 0; j < n; j++) {
+    for (k = Pp[j]; k < Pp[j + 1]; k++) {
+      i = Pi[k];
+      if (i != j) {
+        pos      = next[j]++;
+        ci[pos]  = i;
+        vx[pos]  = Px[k];
+        map_l[k] = pos;
+      } else {
+        map_l[k] = -1;
+      }
+    }
+  }
+  /* missing diagonals sit between the lower and the upper part */
+  for (i = 0; i < n; i++) {
+    if (!has_diag[i]) {
+      pos     = next[i]++;
+      ci[pos] = i;
+      vx[pos] = 0.0;
+    }
+  }
+  /* pass 2: the upper triangle itself, row i receives columns j >= i in ascending j */
+  for (j = 0; j < n; j++) {
+    for (k = Pp[j]; k < Pp[j + 1]; k++) {
+      i        = Pi[k];
+      pos      = next[i]++;
+      ci[pos]  = j;
+      vx[pos]  = Px[k];
+      map_u[k] = pos;
+    }
+  }
+  (void)nnz;
+  out = b200_csr_create((int)n, (int)n, (int)nnz_full, rp, ci, vx);
+
+done:
+  c_free(rp); c_free(next); c_free(has_diag); c_free(ci); c_free(vx);
+  return out;
+}
+
+OSQPMatrix* OSQPMatrix_new_from_csc(const OSQPCscMatrix* M, OSQPInt is_triu) {
+  OSQPInt     nnz = M->p[M->n];
+  OSQPMatrix* out = (OSQPMatrix*)c_calloc(1, sizeof(OSQPMatrix));
+  if (!out) return OSQP_NULL;
+
+  out->m            = M->m;
+  out->n            = M->n;
+  out->nnz_user     = nnz;
+  out->is_symmetric = is_triu ? 1 : 0;
+  out->h_map        = (OSQPInt*)c_malloc(((size_t)nnz + 1) * sizeof(OSQPInt));
+  if (!out->h_map) goto fail;
+
+  if (is_triu) {
+    out->h_map2 = (OSQPInt*)c_malloc(((size_t)nnz + 1) * sizeof(OSQPInt));
+    if (!out->h_map2) goto fail;
+    out->S  = full_from_triu(M->n, M->p, M->i, M->x, out->h_map, out->h_map2);
+    out->St = OSQP_NULL;
+    if (!out->S) goto fail;
+  } else {
+    /* CSC(A) == CSR(A') */
+    out->St = b200_csr_create((int)M->n, (int)M->m, (int)nnz, M->p, M->i, M->x);
+    out->S  = csr_from_csc(M->m, M->n, M->p, M->i, M->x, out->h_map);
+    if (!out->S || !out->St) goto fail;
+  }
+  return out;
+
+fail:
+  OSQPMatrix_free(out);
+  return OSQP_NULL;
+}
+
+void OSQPMatrix_free(OSQPMatrix* M) {
+  if (M) {
+    b200_csr_destroy(M->S);
+    b200_csr_destroy(M->St);
+    c_free(M->h_map);
+    c_free(M->h_map2);
+    c_free(M);
+  }
+}
+
+/* ------------------------------------------------------------------ accessors */
+
+OSQPInt OSQPMatrix_get_m(const OSQPMatrix* M) { return M->m; }
+OSQPInt OSQPMatrix_get_n(const OSQPMatrix* M) { return M->n; }
+/* triu count for P: osqp_update_data_mat validates against it (osqp_api.c:1333-1347) */
+OSQPInt OSQPMatrix_get_nz(const OSQPMatrix* M) { return M->nnz_user; }
+
+OSQPInt OSQPMatrix_is_eq(const OSQPMatrix* A, const OSQPMatrix* B, OSQPFloat tol) {
+  if (A->is_symmetric != B->is_symmetric) return 0;
+  return b200_csr_is_eq(A->S, B->S, tol);
+}
+
+/* ---------------------------------------------------------------- value update
+ * Mx_new_idx indexes the USER's CSC value array (triu for P); NULL = all values in CSC order
+ * (algebra/_common/csc_math.c:27-45). */
+void OSQPMatrix_update_values(OSQPMatrix* M, const OSQPFloat* Mx_new, const OSQPInt* Mx_new_idx,
+                              OSQPInt M_new_n) {
+  OSQPInt    k, cnt, nl;
+  OSQPInt*   h_idx  = OSQP_NULL;
+  OSQPInt*   h_idx2 = OSQP_NULL;
+  OSQPInt*   h_sel  = OSQP_NULL;
+  OSQPFloat* d_x    = OSQP_NULL;
+  OSQPFloat* d_x2   = OSQP_NULL;
+  OSQPInt*   d_idx  = OSQP_NULL;
+
+  cnt = Mx_new_idx ? M_new_n : M->nnz_user;
+  if (cnt <= 0) return;
+
+  d_x   = (OSQPFloat*)b200_malloc((size_t)cnt * sizeof(OSQPFloat));
+  d_idx = (OSQPInt*)b200_malloc((size_t)cnt * sizeof(OSQPInt));
+  h_idx = (OSQPInt*)c_malloc((size_t)cnt * sizeof(OSQPInt));
+  if (!d_x || !d_idx || !h_idx) goto done;
+  b200_copy_in(d_x, Mx_new, (size_t)cnt * sizeof(OSQPFloat));
+
+  /* positions in S (for P: the upper copy) */
+  for (k = 0; k < cnt; k++) h_idx[k] = M->h_map[Mx_new_idx ? Mx_new_idx[k] : k];
+  b200_copy_in(d_idx, h_idx, (size_t)cnt * sizeof(OSQPInt));
+  b200_vec_scatter(b200_csr_values(M->S), d_x, d_idx, (int)cnt);
+
+  if (!M->is_symmetric) {
+    /* A' shares the user's CSC ordering */
+    if (!Mx_new_idx) {
+      b200_copy_in(b200_csr_values(M->St), d_x, (size_t)cnt * sizeof(OSQPFloat));
+    } else {
+      b200_sync();   /* h_idx was the staging source of the previous copy */
+      b200_copy_in(d_idx, Mx_new_idx, (size_t)cnt * sizeof(OSQPInt));
+      b200_vec_scatter(b200_csr_values(M->St), d_x, d_idx, (int)cnt);
+    }
+  } else {
+    /* mirrored (strictly lower) copies */
+    h_idx2 = (OSQPInt*)c_malloc((size_t)cnt * sizeof(OSQPInt));
+    h_sel  = (OSQPInt*)c_malloc((size_t)cnt * sizeof(OSQPInt));
+    if (!h_idx2 || !h_sel) goto done;
+    nl = 0;
+    for (k = 0; k < cnt; k++) {
+      OSQPInt pos = M->h_map2[Mx_new_idx ? Mx_new_idx[k] : k];
+      if (pos >= 0) {
+        h_idx2[nl] = pos;
+        h_sel[nl]  = k;
+        nl++;
+      }
+    }
+    if (nl > 0) {
+      d_x2 = (OSQPFloat*)b200_malloc((size_t)nl * sizeof(OSQPFloat));
+      if (!d_x2) goto done;
+      b200_sync();
+      b200_copy_in(d_idx, h_sel, (size_t)nl * sizeof(OSQPInt));
+      b200_vec_gather(d_x2, d_x, d_idx, (int)nl);
+      b200_sync();
+      b200_copy_in(d_idx, h_idx2, (size_t)nl * sizeof(OSQPInt));
+      b200_vec_scatter(b200_csr_values(M->S), d_x2, d_idx, (int)nl);
+    }
+  }
+
+done:
+  b200_sync();
+  b200_free(d_x); b200_free(d_x2); b200_free(d_idx);
+  c_free(h_idx); c_free(h_idx2); c_free(h_sel);
+}
+
+/* ------------------------------------------------------------------- scalings */
+
+void OSQPMatrix_mult_scalar(OSQPMatrix* A, OSQPFloat sc) {
+  b200_csr_scale(A->S, sc);
+  if (A->St) b200_csr_scale(A->St, sc);
+}
+
+/* A = diag(L) A : rows of A, columns of A' */
+void OSQPMatrix_lmult_diag(OSQPMatrix* A, const OSQPVectorf* L) {
+  b200_csr_scale_rows(A->S, L->d_val);
+  if (A->St) b200_csr_scale_cols(A->St, L->d_val);
+}
+
+/* A = A diag(R) : columns of A, rows of A' */
+void OSQPMatrix_rmult_diag(OSQPMatrix* A, const OSQPVectorf* R) {
+  b200_csr_scale_cols(A->S, R->d_val);
+  if (A->St) b200_csr_scale_rows(A->St, R->d_val);
+}
+
+/* ------------------------------------------------------------------- products */
+
+/* y = alpha A x + beta y.  For P the full symmetric CSR makes this the symmetric product
+ * that csc_Axpy_sym_triu computes on the CPU (csc_math.c:114-166). */
+void OSQPMatrix_Axpy(const OSQPMatrix* A, const OSQPVectorf* x, OSQPVectorf* y, OSQPFloat alpha,
+                     OSQPFloat beta) {
+  if (y->length <= 0) return;
+  b200_csr_spmv(A->S, x->d_val, y->d_val, alpha, beta);
+}
+
+/* y = alpha A' x + beta y through the stored transpose (no atomics) */
+void OSQPMatrix_Atxpy(const OSQPMatrix* A, const OSQPVectorf* x, OSQPVectorf* y, OSQPFloat alpha,
+                      OSQPFloat beta) {
+  if (y->length <= 0) return;
+  b200_csr_spmv(A->is_symmetric ? A->S : A->St, x->d_val, y->d_val, alpha, beta);
+}
+
+/* ---------------------------------------------------------------------- norms */
+
+void OSQPMatrix_col_norm_inf(const OSQPMatrix* M, OSQPVectorf* E) {
+  /* columns of A are rows of A'; P is symmetric */
+  b200_csr_row_absmax(M->is_symmetric ? M->S : M->St, E->d_val);
+}
+
+void OSQPMatrix_row_norm_inf(const OSQPMatrix* M, OSQPVectorf* E) {
+  b200_csr_row_absmax(M->S, E->d_val);
+}
+
+/* ------------------------------------------------------------ row extraction
+ * keeps row j iff rows[j] != 0, order preserved (csc_utils.c:134-203); used by polish only,
+ * so it goes through the host. */
+OSQPMatrix* OSQPMatrix_submatrix_byrows(const OSQPMatrix* A, const OSQPVectori* rows) {
+  OSQPInt        m = A->m, n = A->n, nnz = A->nnz_user;
+  OSQPInt        i, j, k, mred = 0, nzred = 0;
+  OSQPMatrix*    out   = OSQP_NULL;
+  OSQPInt*       flags = OSQP_NULL;
+  OSQPInt*       newrow = OSQP_NULL;
+  OSQPInt *Ap = OSQP_NULL, *Ai = OSQP_NULL, *Rp = OSQP_NULL, *Ri = OSQP_NULL;
+  OSQPFloat *Ax = OSQP_NULL, *Rx = OSQP_NULL;
+  OSQPCscMatrix R;
+
+  if (A->is_symmetric) {
+    c_eprint("row selection not implemented for partially filled matrices");
+    return OSQP_NULL;
+  }
+
+  flags  = (OSQPInt*)c_malloc(((size_t)m + 1) * sizeof(OSQPInt));
+  newrow = (OSQPInt*)c_malloc(((size_t)m + 1) * sizeof(OSQPInt));
+  Ap = (OSQPInt*)c_malloc(((size_t)n + 1) * sizeof(OSQPInt));
+  Ai = (OSQPInt*)c_malloc(((size_t)nnz + 1) * sizeof(OSQPInt));
+  Ax = (OSQPFloat*)c_malloc(((size_t)nnz + 1) * sizeof(OSQPFloat));
+  Rp = (OSQPInt*)c_malloc(((size_t)n + 1) * sizeof(OSQPInt));
+  Ri = (OSQPInt*)c_malloc(((size_t)nnz + 1) * sizeof(OSQPInt));
+  Rx = (OSQPFloat*)c_malloc(((size_t)nnz + 1) * sizeof(OSQPFloat));
+  if (!flags || !newrow || !Ap || !Ai || !Ax || !Rp || !Ri || !Rx) goto done;
+
+  if (m > 0) b200_copy_out(flags, rows->d_val, (size_t)m * sizeof(OSQPInt));
+  /* CSR of A' == CSC of A (current, i.e. scaled, values) */
+  if (b200_csr_download(A->St, Ap, Ai, Ax)) goto done;
+
+  for (i = 0; i < m; i++) newrow[i] = flags[i] ? mred++ : -1;
+  for (j = 0; j < n; j++) {
+    Rp[j] = nzred;
+    for (k = Ap[j]; k < Ap[j + 1]; k++) {
+      if (newrow[Ai[k]] >= 0) {
+        Ri[nzred] = newrow[Ai[k]];
+        Rx[nzred] = Ax[k];
+        nzred++;
+      }
+    }
+  }
+  Rp[n] = nzred;
+
+  memset(&R, 0, sizeof(R));
+  R.m = mred; R.n = n; R.p = Rp; R.i = Ri; R.x = Rx; R.nzmax = nzred; R.nz = -1;
+  out = OSQPMatrix_new_from_csc(&R, 0);
+
+done:
+  c_free(flags); c_free(newrow); c_free(Ap); c_free(Ai); c_free(Ax);
+  c_free(Rp); c_free(Ri); c_free(Rx);
+  return out;
+}

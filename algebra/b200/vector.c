@@ -1,0 +1,271 @@
+/*
+ * algebra/b200/vector.c -- OSQPVectorf / OSQPVectori over B200 device memory.
+ *
+ * Implements /root/reference/include/private/algebra_vector.h:28-290.  Semantics follow the
+ * CPU reference (algebra/builtin/vector.c), which is the parity oracle; the structure of the
+ * container (device array + view flag, host-or-device raw pointers) follows the role of
+ * algebra/cuda/vector.cu:43-237.  Every numerical operation is one call into the C-ABI
+ * (include/osqp_b200.h) and therefore one sm_100a kernel on the library stream.
+ */
+#include "osqp.h"
+#include "algebra_vector.h"
+#include "algebra_impl.h"
+#include "glob_opts.h"
+
+/* ------------------------------------------------------------------ creation */
+
+OSQPVectorf* OSQPVectorf_malloc(OSQPInt length) {
+  OSQPVectorf* b = (OSQPVectorf*)c_malloc(sizeof(OSQPVectorf));
+  if (!b) return OSQP_NULL;
+  b->length  = length;
+  b->is_view = 0;
+  b->d_val   = (OSQPFloat*)b200_malloc((size_t)length * sizeof(OSQPFloat));
+  if (!b->d_val) {
+    c_free(b);
+    return OSQP_NULL;
+  }
+  return b;
+}
+
+OSQPVectorf* OSQPVectorf_calloc(OSQPInt length) {
+  OSQPVectorf* b = (OSQPVectorf*)c_malloc(sizeof(OSQPVectorf));
+  if (!b) return OSQP_NULL;
+  b->length  = length;
+  b->is_view = 0;
+  b->d_val   = (OSQPFloat*)b200_calloc((size_t)length * sizeof(OSQPFloat));
+  if (!b->d_val) {
+    c_free(b);
+    return OSQP_NULL;
+  }
+  return b;
+}
+
+OSQPVectori* OSQPVectori_malloc(OSQPInt length) {
+  OSQPVectori* b = (OSQPVectori*)c_malloc(sizeof(OSQPVectori));
+  if (!b) return OSQP_NULL;
+  b->length = length;
+  b->d_val  = (OSQPInt*)b200_malloc((size_t)length * sizeof(OSQPInt));
+  if (!b->d_val) {
+    c_free(b);
+    return OSQP_NULL;
+  }
+  return b;
+}
+
+OSQPVectori* OSQPVectori_calloc(OSQPInt length) {
+  OSQPVectori* b = (OSQPVectori*)c_malloc(sizeof(OSQPVectori));
+  if (!b) return OSQP_NULL;
+  b->length = length;
+  b->d_val  = (OSQPInt*)b200_calloc((size_t)length * sizeof(OSQPInt));
+  if (!b->d_val) {
+    c_free(b);
+    return OSQP_NULL;
+  }
+  return b;
+}
+
+OSQPVectorf* OSQPVectorf_new(const OSQPFloat* a, OSQPInt length) {
+  OSQPVectorf* out = OSQPVectorf_malloc(length);
+  if (!out) return OSQP_NULL;
+  if (length > 0) OSQPVectorf_from_raw(out, a);
+  return out;
+}
+
+OSQPVectori* OSQPVectori_new(const OSQPInt* a, OSQPInt length) {
+  OSQPVectori* out = OSQPVectori_malloc(length);
+  if (!out) return OSQP_NULL;
+  if (length > 0) OSQPVectori_from_raw(out, a);
+  return out;
+}
+
+OSQPVectorf* OSQPVectorf_copy_new(const OSQPVectorf* a) {
+  OSQPVectorf* b = OSQPVectorf_malloc(a->length);
+  if (b) OSQPVectorf_copy(b, a);
+  return b;
+}
+
+void OSQPVectorf_free(OSQPVectorf* a) {
+  if (a) {
+    if (!a->is_view) b200_free(a->d_val);
+    c_free(a);
+  }
+}
+
+void OSQPVectori_free(OSQPVectori* a) {
+  if (a) {
+    b200_free(a->d_val);
+    c_free(a);
+  }
+}
+
+/* views alias the parent's device storage (xtilde/ztilde inside xz_tilde, osqp_api.c:420-421) */
+OSQPVectorf* OSQPVectorf_view(const OSQPVectorf* a, OSQPInt head, OSQPInt length) {
+  OSQPVectorf* view = (OSQPVectorf*)c_malloc(sizeof(OSQPVectorf));
+  if (view) {
+    view->length  = length;
+    view->is_view = 1;
+    view->d_val   = a->d_val + head;
+  }
+  return view;
+}
+
+void OSQPVectorf_view_update(OSQPVectorf* a, const OSQPVectorf* b, OSQPInt head, OSQPInt length) {
+  a->length = length;
+  a->d_val  = b->d_val + head;
+}
+
+void OSQPVectorf_view_free(OSQPVectorf* a) {
+  if (a) c_free(a);
+}
+
+OSQPInt OSQPVectorf_length(const OSQPVectorf* a) { return a->length; }
+OSQPInt OSQPVectori_length(const OSQPVectori* a) { return a->length; }
+
+/* device pointer; only meaningful to device-aware callers */
+OSQPFloat* OSQPVectorf_data(const OSQPVectorf* a) { return a->d_val; }
+
+/* ---------------------------------------------------------------- raw copies */
+
+void OSQPVectorf_copy(OSQPVectorf* b, const OSQPVectorf* a) {
+  if (b == a) return;
+  b200_copy_in(b->d_val, a->d_val, (size_t)a->length * sizeof(OSQPFloat));
+}
+
+/* `a` / `bv` may be host or device memory (reference: algebra/cuda/vector.cu:195-237) */
+void OSQPVectorf_from_raw(OSQPVectorf* b, const OSQPFloat* a) {
+  b200_copy_in(b->d_val, a, (size_t)b->length * sizeof(OSQPFloat));
+}
+
+void OSQPVectori_from_raw(OSQPVectori* b, const OSQPInt* a) {
+  b200_copy_in(b->d_val, a, (size_t)b->length * sizeof(OSQPInt));
+}
+
+void OSQPVectorf_to_raw(OSQPFloat* bv, const OSQPVectorf* a) {
+  b200_copy_out(bv, a->d_val, (size_t)a->length * sizeof(OSQPFloat));
+}
+
+void OSQPVectori_to_raw(OSQPInt* bv, const OSQPVectori* a) {
+  b200_copy_out(bv, a->d_val, (size_t)a->length * sizeof(OSQPInt));
+}
+
+/* ------------------------------------------------------------- elementwise ops */
+
+OSQPInt OSQPVectorf_is_eq(const OSQPVectorf* A, const OSQPVectorf* B, OSQPFloat tol) {
+  if (A->length != B->length) return 0;
+  return b200_vec_is_eq(A->d_val, B->d_val, tol, A->length);
+}
+
+void OSQPVectorf_set_scalar(OSQPVectorf* a, OSQPFloat sc) {
+  b200_vec_set_scalar(a->d_val, sc, a->length);
+}
+
+void OSQPVectorf_set_scalar_conditional(OSQPVectorf* a, const OSQPVectori* test,
+                                        OSQPFloat val_if_neg, OSQPFloat val_if_zero,
+                                        OSQPFloat val_if_pos) {
+  b200_vec_set_scalar_cond(a->d_val, test->d_val, val_if_neg, val_if_zero, val_if_pos, a->length);
+}
+
+void OSQPVectorf_round_to_zero(OSQPVectorf* a, OSQPFloat tol) {
+  b200_vec_round_to_zero(a->d_val, tol, a->length);
+}
+
+void OSQPVectorf_mult_scalar(OSQPVectorf* a, OSQPFloat sc) {
+  b200_vec_mult_scalar(a->d_val, sc, a->length);
+}
+
+void OSQPVectorf_plus(OSQPVectorf* x, const OSQPVectorf* a, const OSQPVectorf* b) {
+  b200_vec_add_scaled(x->d_val, 1.0, a->d_val, 1.0, b->d_val, a->length);
+}
+
+void OSQPVectorf_minus(OSQPVectorf* x, const OSQPVectorf* a, const OSQPVectorf* b) {
+  b200_vec_add_scaled(x->d_val, 1.0, a->d_val, -1.0, b->d_val, a->length);
+}
+
+void OSQPVectorf_add_scaled(OSQPVectorf* x, OSQPFloat sca, const OSQPVectorf* a, OSQPFloat scb,
+                            const OSQPVectorf* b) {
+  b200_vec_add_scaled(x->d_val, sca, a->d_val, scb, b->d_val, x->length);
+}
+
+void OSQPVectorf_add_scaled3(OSQPVectorf* x, OSQPFloat sca, const OSQPVectorf* a, OSQPFloat scb,
+                             const OSQPVectorf* b, OSQPFloat scc, const OSQPVectorf* c) {
+  b200_vec_add_scaled3(x->d_val, sca, a->d_val, scb, b->d_val, scc, c->d_val, x->length);
+}
+
+void OSQPVectorf_ew_prod(OSQPVectorf* c, const OSQPVectorf* a, const OSQPVectorf* b) {
+  b200_vec_ew_prod(c->d_val, a->d_val, b->d_val, c->length);
+}
+
+void OSQPVectorf_ew_bound_vec(OSQPVectorf* x, const OSQPVectorf* z, const OSQPVectorf* l,
+                              const OSQPVectorf* u) {
+  b200_vec_ew_bound(x->d_val, z->d_val, l->d_val, u->d_val, x->length);
+}
+
+void OSQPVectorf_project_polar_reccone(OSQPVectorf* y, const OSQPVectorf* l, const OSQPVectorf* u,
+                                       OSQPFloat infval) {
+  b200_vec_project_polar_reccone(y->d_val, l->d_val, u->d_val, infval, y->length);
+}
+
+void OSQPVectorf_ew_reciprocal(OSQPVectorf* b, const OSQPVectorf* a) {
+  b200_vec_ew_reciprocal(b->d_val, a->d_val, a->length);
+}
+
+void OSQPVectorf_ew_sqrt(OSQPVectorf* a) { b200_vec_ew_sqrt(a->d_val, a->length); }
+
+void OSQPVectorf_ew_max_vec(OSQPVectorf* c, const OSQPVectorf* a, const OSQPVectorf* b) {
+  b200_vec_ew_max(c->d_val, a->d_val, b->d_val, c->length);
+}
+
+void OSQPVectorf_ew_min_vec(OSQPVectorf* c, const OSQPVectorf* a, const OSQPVectorf* b) {
+  b200_vec_ew_min(c->d_val, a->d_val, b->d_val, c->length);
+}
+
+void OSQPVectorf_set_scalar_if_lt(OSQPVectorf* x, const OSQPVectorf* z, OSQPFloat testval,
+                                  OSQPFloat newval) {
+  b200_vec_set_scalar_if_lt(x->d_val, z->d_val, testval, newval, x->length);
+}
+
+void OSQPVectorf_set_scalar_if_gt(OSQPVectorf* x, const OSQPVectorf* z, OSQPFloat testval,
+                                  OSQPFloat newval) {
+  b200_vec_set_scalar_if_gt(x->d_val, z->d_val, testval, newval, x->length);
+}
+
+/* ------------------------------------------------------------------ reductions
+ * each returns a host scalar by value and is therefore one stream synchronisation */
+
+OSQPFloat OSQPVectorf_norm_inf(const OSQPVectorf* v) {
+  return b200_vec_norm_inf(v->d_val, v->length);
+}
+
+OSQPFloat OSQPVectorf_scaled_norm_inf(const OSQPVectorf* S, const OSQPVectorf* v) {
+  return b200_vec_scaled_norm_inf(S->d_val, v->d_val, v->length);
+}
+
+OSQPFloat OSQPVectorf_norm_inf_diff(const OSQPVectorf* a, const OSQPVectorf* b) {
+  return b200_vec_norm_inf_diff(a->d_val, b->d_val, a->length);
+}
+
+OSQPFloat OSQPVectorf_norm_1(const OSQPVectorf* a) { return b200_vec_norm_1(a->d_val, a->length); }
+
+OSQPFloat OSQPVectorf_norm_2(const OSQPVectorf* a) { return b200_vec_norm_2(a->d_val, a->length); }
+
+OSQPFloat OSQPVectorf_dot_prod(const OSQPVectorf* a, const OSQPVectorf* b) {
+  return b200_vec_dot(a->d_val, b->d_val, a->length);
+}
+
+OSQPFloat OSQPVectorf_dot_prod_signed(const OSQPVectorf* a, const OSQPVectorf* b, OSQPInt sign) {
+  return b200_vec_dot_signed(a->d_val, b->d_val, (int)sign, a->length);
+}
+
+OSQPInt OSQPVectorf_all_leq(const OSQPVectorf* l, const OSQPVectorf* u) {
+  return b200_vec_all_leq(l->d_val, u->d_val, l->length);
+}
+
+OSQPInt OSQPVectorf_in_reccone(const OSQPVectorf* y, const OSQPVectorf* l, const OSQPVectorf* u,
+                               OSQPFloat infval, OSQPFloat tol) {
+  return b200_vec_in_reccone(y->d_val, l->d_val, u->d_val, infval, tol, y->length);
+}
+
+OSQPInt OSQPVectorf_ew_bounds_type(OSQPVectori* iseq, const OSQPVectorf* l, const OSQPVectorf* u,
+                                   OSQPFloat tol, OSQPFloat infval) {
+  return b200_vec_bounds_type(iseq->d_val, l->d_val, u->d_val, tol, infval, iseq->length);
+}

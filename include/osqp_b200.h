@@ -1,0 +1,200 @@
+/*
+ * osqp_b200.h -- C-ABI of the B200 (sm_100a) kernel library behind OSQP's
+ * `algebra/b200` linear-algebra backend.
+ *
+ * Everything here is `extern "C"`, plain pointers and sizes.  The plain-C backend
+ * in algebra/b200/ implements OSQP's private algebra interface
+ * (/root/reference/include/private/{lin_alg,algebra_vector,algebra_matrix}.h and the
+ * LinSysSolver vtable, include/private/types.h:243-279) on top of these entry
+ * points; every function cites the reference interface / implementation whose
+ * role it takes over.  No cuSPARSE / cuBLAS / thrust is used anywhere below.
+ *
+ * Conventions
+ *   - `b200_float` is OSQPFloat (double, or float with -DB200_USE_FLOAT), `int` is
+ *     OSQPInt (32-bit).  The library is compiled once per precision.
+ *   - pointers named d_* are device pointers; h_* host pointers; others are
+ *     "host or device" and are classified at run time (reference:
+ *     algebra/cuda/src/cuda_memory.cu:72-112).
+ *   - all work is enqueued on ONE library stream; functions that return a scalar
+ *     by value synchronise that stream, nothing else does.
+ *   - functions returning int return 0 on success, non-zero on failure, and never
+ *     abort the process (the reference aborts: algebra/cuda/include/helper_cuda.h:584-597).
+ */
+#ifndef OSQP_B200_H
+#define OSQP_B200_H
+
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#ifdef B200_USE_FLOAT
+typedef float b200_float;
+#else
+typedef double b200_float;
+#endif
+
+/* ------------------------------------------------------------------ lifecycle
+ * replaces osqp_algebra_init_libs / free_libs / device_name
+ * (algebra/cuda/algebra_libs.cu:31-75, src/cuda_handler.cu:22-44).  Ref-counted so that
+ * several solvers can be alive at once (osqp_cleanup calls free_libs, osqp_api.c:1068). */
+int  b200_init(int device);              /* 0 ok; 1 = no usable GPU                 */
+void b200_shutdown(void);
+int  b200_device_name(char* name, int len);
+int  b200_sm_count(void);
+void b200_sync(void);                    /* wait for the library stream             */
+void* b200_stream_handle(void);          /* cudaStream_t of the library stream      */
+int  b200_last_error(void);              /* sticky CUDA error code, 0 if none       */
+unsigned long long b200_launch_count(void); /* kernels launched since b200_init      */
+
+/* --------------------------------------------------------------------- memory
+ * replaces cuda_malloc/cuda_calloc/cuda_free + cuda_vec_copy_{h2d,d2h,d2d}
+ * (algebra/cuda/src/cuda_memory.cu, src/cuda_lin_alg.cu:520-560). */
+void* b200_malloc(size_t bytes);
+void* b200_calloc(size_t bytes);
+void  b200_free(void* d_ptr);
+int   b200_copy_in (void* d_dst, const void* src, size_t bytes);   /* src: host or device */
+int   b200_copy_out(void* dst, const void* d_src, size_t bytes);   /* dst: host or device */
+int   b200_ptr_is_device(const void* ptr);
+
+/* ------------------------------------------------------------- vector kernels
+ * one templated grid-stride kernel family; replaces the 19 elementwise kernels of
+ * algebra/cuda/src/cuda_lin_alg.cu:38-358 and the cublas axpy/scal/copy call sites
+ * (:543-677).  In-place aliasing (x == a) is allowed everywhere
+ * (include/private/algebra_vector.h:146-170,202-220). */
+void b200_vec_set_scalar(b200_float* d_a, b200_float sc, int n);
+void b200_vec_set_scalar_cond(b200_float* d_a, const int* d_test, b200_float neg,
+                              b200_float zero, b200_float pos, int n);
+void b200_vec_round_to_zero(b200_float* d_a, b200_float tol, int n);
+void b200_vec_mult_scalar(b200_float* d_a, b200_float sc, int n);
+void b200_vec_add_scaled(b200_float* d_x, b200_float sca, const b200_float* d_a,
+                         b200_float scb, const b200_float* d_b, int n);
+void b200_vec_add_scaled3(b200_float* d_x, b200_float sca, const b200_float* d_a,
+                          b200_float scb, const b200_float* d_b,
+                          b200_float scc, const b200_float* d_c, int n);
+void b200_vec_ew_prod(b200_float* d_c, const b200_float* d_a, const b200_float* d_b, int n);
+void b200_vec_ew_bound(b200_float* d_x, const b200_float* d_z, const b200_float* d_l,
+                       const b200_float* d_u, int n);
+void b200_vec_project_polar_reccone(b200_float* d_y, const b200_float* d_l,
+                                    const b200_float* d_u, b200_float infval, int n);
+void b200_vec_ew_reciprocal(b200_float* d_b, const b200_float* d_a, int n);
+void b200_vec_ew_sqrt(b200_float* d_a, int n);
+void b200_vec_ew_max(b200_float* d_c, const b200_float* d_a, const b200_float* d_b, int n);
+void b200_vec_ew_min(b200_float* d_c, const b200_float* d_a, const b200_float* d_b, int n);
+void b200_vec_set_scalar_if_lt(b200_float* d_x, const b200_float* d_z, b200_float testval,
+                               b200_float newval, int n);
+void b200_vec_set_scalar_if_gt(b200_float* d_x, const b200_float* d_z, b200_float testval,
+                               b200_float newval, int n);
+void b200_vec_scatter(b200_float* d_dst, const b200_float* d_src, const int* d_idx, int n);
+void b200_vec_gather(b200_float* d_dst, const b200_float* d_src, const int* d_idx, int n);
+
+/* reductions: warp-shuffle -> one partial per CTA -> last CTA finishes in fixed order
+ * (deterministic); the scalar lands in a pinned slot and is returned by value.
+ * replaces cublasI?amax(+abs_kernel), cublas?dot/asum/nrm2 and the cudaMalloc'ing
+ * helpers at algebra/cuda/src/cuda_lin_alg.cu:679-780,792-958. */
+b200_float b200_vec_norm_inf(const b200_float* d_v, int n);
+b200_float b200_vec_scaled_norm_inf(const b200_float* d_s, const b200_float* d_v, int n);
+b200_float b200_vec_norm_inf_diff(const b200_float* d_a, const b200_float* d_b, int n);
+b200_float b200_vec_norm_1(const b200_float* d_v, int n);
+b200_float b200_vec_norm_2(const b200_float* d_v, int n);
+b200_float b200_vec_dot(const b200_float* d_a, const b200_float* d_b, int n);
+b200_float b200_vec_dot_signed(const b200_float* d_a, const b200_float* d_b, int sign, int n);
+int b200_vec_all_leq(const b200_float* d_l, const b200_float* d_u, int n);
+int b200_vec_in_reccone(const b200_float* d_y, const b200_float* d_l, const b200_float* d_u,
+                        b200_float infval, b200_float tol, int n);
+int b200_vec_is_eq(const b200_float* d_a, const b200_float* d_b, b200_float tol, int n);
+int b200_veci_is_eq(const int* d_a, const int* d_b, int n);
+/* constraint classification; returns 1 iff any entry of d_iseq changed
+ * (algebra/builtin/vector.c:888-922) */
+int b200_vec_bounds_type(int* d_iseq, const b200_float* d_l, const b200_float* d_u,
+                         b200_float tol, b200_float infval, int n);
+
+/* ------------------------------------------------------------------ CSR matrix
+ * One device CSR matrix (int32 indices) plus its row-block schedule for the
+ * "CSR-stream" SpMV: contiguous row blocks of <= B200_SPMV_TILE nonzeros are staged
+ * through shared memory by one CTA; rows longer than a tile are split over several
+ * CTAs and summed in fixed order by the last arriving CTA (no floating-point atomics).
+ * replaces `csr` + cusparseSpMV (algebra/cuda/include/csr_type.h:27-40,
+ * src/cuda_lin_alg.cu:1053-1063) and the row-wise thrust reductions (:465-498). */
+typedef struct b200_csr b200_csr;
+
+b200_csr* b200_csr_create(int nrows, int ncols, int nnz, const int* h_row_ptr,
+                          const int* h_col_ind, const b200_float* h_val);
+void b200_csr_destroy(b200_csr* M);
+int  b200_csr_nrows(const b200_csr* M);
+int  b200_csr_ncols(const b200_csr* M);
+int  b200_csr_nnz(const b200_csr* M);
+b200_float* b200_csr_values(b200_csr* M);                 /* device value array        */
+int  b200_csr_download(const b200_csr* M, int* h_row_ptr, int* h_col_ind, b200_float* h_val);
+/* d_y = alpha * M * d_x + beta * d_y   (beta == 0 overwrites: csc_math.c:183) */
+void b200_csr_spmv(const b200_csr* M, const b200_float* d_x, b200_float* d_y,
+                   b200_float alpha, b200_float beta);
+void b200_csr_scale(b200_csr* M, b200_float sc);                    /* M *= sc          */
+void b200_csr_scale_rows(b200_csr* M, const b200_float* d_L);       /* M = diag(L) M    */
+void b200_csr_scale_cols(b200_csr* M, const b200_float* d_R);       /* M = M diag(R)    */
+void b200_csr_row_absmax(const b200_csr* M, b200_float* d_out);     /* max_j |M_ij|     */
+/* d_out[i] = sum_j M_ij^2 * w_j   (w == NULL -> w_j = w_scalar): Jacobi diagonal of A' R A
+ * when M = A' (algebra/cuda/lin_sys/indirect/cuda_pcg.cu:236-251) */
+void b200_csr_row_wsumsq(const b200_csr* M, const b200_float* d_w, b200_float w_scalar,
+                         b200_float* d_out);
+void b200_csr_diag(const b200_csr* M, b200_float* d_out);            /* 0 where absent   */
+int  b200_csr_is_eq(const b200_csr* A, const b200_csr* B, b200_float tol);
+
+/* ------------------------------------------------------ reduced-KKT PCG solver
+ * Jacobi-preconditioned CG on K = P + sigma I + A' diag(rho) A, run as ONE persistent
+ * cooperative kernel per ADMM iteration: reduced right-hand side, tolerance schedule,
+ * the CG loop (convergence decided on device) and z~ = A x~ all happen without a single
+ * host synchronisation.  replaces solve_linsys_cudapcg / cuda_pcg_alg / mat_vec_prod /
+ * compute_tolerance (algebra/cuda/lin_sys/indirect/cuda_pcg_interface.cu:32-92,229-273,
+ * cuda_pcg.cu:50-208): ~17 launches + 1 device sync per CG iteration there. */
+typedef struct b200_pcg b200_pcg;
+
+/* P: full symmetric n x n CSR with structurally full diagonal; A: m x n CSR; At: n x m CSR.
+ * The solver borrows the matrices (sees in-place value updates after
+ * b200_pcg_refresh_matrices). */
+b200_pcg* b200_pcg_create(const b200_csr* P, const b200_csr* A, const b200_csr* At,
+                          int n, int m);
+void b200_pcg_destroy(b200_pcg* s);
+/* sigma, scalar rho, optional device rho vector (NULL -> scalar), preconditioner
+ * (0 none / 1 Jacobi), polishing flag */
+void b200_pcg_configure(b200_pcg* s, b200_float sigma, b200_float rho,
+                        const b200_float* d_rho_vec, int precond, int polishing);
+/* rebuild the fused operator [P + sigma I | A'] values / the Jacobi diagonal after P, A
+ * or rho changed (cuda_pcg_update_precond, cuda_pcg.cu:211-284) */
+void b200_pcg_refresh_matrices(b200_pcg* s);
+void b200_pcg_refresh_precond(b200_pcg* s);
+void b200_pcg_warm_start(b200_pcg* s, const b200_float* d_x);
+/* In place on d_b (length n+m): in = KKT right-hand side (b1, b2); out = (x~, z~ = A x~),
+ * or (x, (A x - b2) / delta) when polishing.  prim_res/dual_res are the host values of
+ * work->scaled_prim_res / scaled_dual_res at call time (types.h:199-200). Asynchronous. */
+int  b200_pcg_solve(b200_pcg* s, b200_float* d_b, int admm_iter, double prim_res,
+                    double dual_res, int max_iter, double tol_fraction,
+                    int reduction_threshold);
+/* synchronising statistics read-back: total CG iterations, number of solves, iterations
+ * and tolerance of the last solve */
+void b200_pcg_stats(b200_pcg* s, long long* total_iters, long long* n_solves,
+                    int* last_iters, double* last_eps, double* last_rnorm);
+
+/* ----------------------------------------------------------- fused ADMM steps
+ * One kernel each instead of the 16 launches of update_x / update_z / update_y
+ * (src/auxil.c:172-229) and the 5 of compute_rhs (src/auxil.c:136-158).
+ * d_rho_vec / d_rho_inv_vec may be NULL (scalar rho). */
+void b200_admm_compute_rhs(b200_float* d_xtilde, b200_float* d_ztilde,
+                           const b200_float* d_x_prev, const b200_float* d_q,
+                           const b200_float* d_z_prev, const b200_float* d_y,
+                           const b200_float* d_rho_inv_vec, b200_float rho_inv,
+                           b200_float sigma, int n, int m);
+void b200_admm_update_xzy(b200_float* d_x, b200_float* d_delta_x, b200_float* d_z,
+                          b200_float* d_y, b200_float* d_delta_y,
+                          const b200_float* d_xtilde, const b200_float* d_ztilde,
+                          const b200_float* d_x_prev, const b200_float* d_z_prev,
+                          const b200_float* d_l, const b200_float* d_u,
+                          const b200_float* d_rho_vec, const b200_float* d_rho_inv_vec,
+                          b200_float rho, b200_float rho_inv, b200_float alpha, int n, int m);
+
+#ifdef __cplusplus
+}
+#endif
+
+#endif /* OSQP_B200_H */

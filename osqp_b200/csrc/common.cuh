@@ -1,0 +1,103 @@
+// common.cuh -- library context, launch helpers, warp/block reduction primitives.
+// sm_100a only.  No cuBLAS / cuSPARSE / thrust.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <cstdio>
+#include <cstdint>
+
+#include "osqp_b200.h"
+
+typedef b200_float T;
+
+namespace b200 {
+
+constexpr int kBlock        = 256;    // threads per CTA for every kernel in the library
+constexpr int kMaxRedBlocks = 1184;   // 148 SMs x 8 CTAs: upper bound for reduction grids
+constexpr int kScalarSlots  = 16;
+
+struct Context {
+  int          refcount   = 0;
+  int          device     = -1;
+  int          sm_count   = 148;
+  cudaStream_t stream     = nullptr;
+  // reduction workspace (device): per-CTA partials, ticket counter
+  double*      d_partials = nullptr;   // kMaxRedBlocks * 4 doubles
+  unsigned*    d_ticket   = nullptr;
+  // result scalars: device slot + pinned host mirror
+  double*      d_scalar   = nullptr;
+  double*      h_scalar   = nullptr;   // pinned
+  // staging buffer for host->device index/value uploads is allocated on demand
+  int          last_error = 0;
+  unsigned long long launches = 0;
+  char         name[256]  = {0};
+};
+
+Context& ctx();
+
+inline bool check(cudaError_t e, const char* what) {
+  if (e != cudaSuccess) {
+    Context& c = ctx();
+    if (!c.last_error) c.last_error = (int)e;
+    fprintf(stderr, "[osqp_b200] CUDA error %d (%s) in %s\n", (int)e, cudaGetErrorString(e), what);
+    return false;
+  }
+  return true;
+}
+
+#define B200_CHECK(expr) ::b200::check((expr), #expr)
+
+inline void count_launch() { ctx().launches++; }
+
+// grid for a grid-stride elementwise kernel: enough CTAs to fill the machine, 4 elements
+// per thread per trip, capped at 8 resident CTAs per SM.
+inline int ew_grid(long long n) {
+  long long want = (n + (long long)kBlock * 4 - 1) / ((long long)kBlock * 4);
+  long long cap  = (long long)ctx().sm_count * 8;
+  if (want < 1) want = 1;
+  return (int)(want < cap ? want : cap);
+}
+
+// ------------------------------------------------------------------ device side
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ double warp_max(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+// Block-wide reductions; result valid in every thread.  `sh` needs >= 33 doubles.
+__device__ __forceinline__ double block_sum(double v, double* sh) {
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  v = warp_sum(v);
+  __syncthreads();
+  if (lane == 0) sh[w] = v;
+  __syncthreads();
+  if (w == 0) {
+    double t = (lane < (blockDim.x >> 5)) ? sh[lane] : 0.0;
+    t = warp_sum(t);
+    if (lane == 0) sh[32] = t;
+  }
+  __syncthreads();
+  return sh[32];
+}
+__device__ __forceinline__ double block_max(double v, double* sh) {
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  v = warp_max(v);
+  __syncthreads();
+  if (lane == 0) sh[w] = v;
+  __syncthreads();
+  if (w == 0) {
+    double t = (lane < (blockDim.x >> 5)) ? sh[lane] : 0.0;
+    t = warp_max(t);
+    if (lane == 0) sh[32] = t;
+  }
+  __syncthreads();
+  return sh[32];
+}
+
+}  // namespace b200

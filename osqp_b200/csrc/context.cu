@@ -1,0 +1,139 @@
+// context.cu -- library lifecycle and memory entry points of the C-ABI.
+// Roles taken over from the reference: osqp_algebra_init_libs/free_libs
+// (algebra/cuda/algebra_libs.cu:31-75, src/cuda_handler.cu:22-44) and the raw memory helpers
+// (algebra/cuda/src/cuda_memory.cu:22-112).
+#include "common.cuh"
+
+#include <cstring>
+
+namespace b200 {
+Context& ctx() {
+  static Context c;
+  return c;
+}
+}  // namespace b200
+
+using namespace b200;
+
+extern "C" {
+
+int b200_init(int device) {
+  Context& c = ctx();
+  if (c.refcount > 0) {
+    c.refcount++;
+    return 0;
+  }
+  int count = 0;
+  if (cudaGetDeviceCount(&count) != cudaSuccess || count <= 0) {
+    cudaGetLastError();
+    fprintf(stderr, "[osqp_b200] no CUDA device visible: the B200 backend has no CPU fallback\n");
+    return 1;
+  }
+  if (device < 0 || device >= count) device = 0;
+  if (!B200_CHECK(cudaSetDevice(device))) return 1;
+  cudaDeviceProp prop;
+  if (!B200_CHECK(cudaGetDeviceProperties(&prop, device))) return 1;
+  c.device   = device;
+  c.sm_count = prop.multiProcessorCount;
+  snprintf(c.name, sizeof(c.name), "%s (sm_%d%d, %d SMs)", prop.name, prop.major, prop.minor,
+           prop.multiProcessorCount);
+  if (!B200_CHECK(cudaStreamCreateWithFlags(&c.stream, cudaStreamNonBlocking))) return 1;
+  bool ok = true;
+  ok &= B200_CHECK(cudaMalloc(&c.d_partials, sizeof(double) * kMaxRedBlocks * 4));
+  ok &= B200_CHECK(cudaMalloc(&c.d_ticket, sizeof(unsigned) * 4));
+  ok &= B200_CHECK(cudaMalloc(&c.d_scalar, sizeof(double) * kScalarSlots));
+  ok &= B200_CHECK(cudaMallocHost(&c.h_scalar, sizeof(double) * kScalarSlots));
+  if (!ok) return 1;
+  B200_CHECK(cudaMemsetAsync(c.d_ticket, 0, sizeof(unsigned) * 4, c.stream));
+  B200_CHECK(cudaMemsetAsync(c.d_scalar, 0, sizeof(double) * kScalarSlots, c.stream));
+  c.last_error = 0;
+  c.launches   = 0;
+  c.refcount   = 1;
+  return 0;
+}
+
+void b200_shutdown(void) {
+  Context& c = ctx();
+  if (c.refcount <= 0) return;
+  if (--c.refcount > 0) return;
+  cudaStreamSynchronize(c.stream);
+  cudaFree(c.d_partials);
+  cudaFree(c.d_ticket);
+  cudaFree(c.d_scalar);
+  cudaFreeHost(c.h_scalar);
+  cudaStreamDestroy(c.stream);
+  c.d_partials = nullptr;
+  c.d_ticket   = nullptr;
+  c.d_scalar   = nullptr;
+  c.h_scalar   = nullptr;
+  c.stream     = nullptr;
+}
+
+int b200_device_name(char* name, int len) {
+  if (!name || len <= 0) return 0;
+  return snprintf(name, (size_t)len, "%s", ctx().refcount > 0 ? ctx().name : "");
+}
+
+int b200_sm_count(void) { return ctx().sm_count; }
+
+void b200_sync(void) {
+  if (ctx().stream) B200_CHECK(cudaStreamSynchronize(ctx().stream));
+}
+
+void* b200_stream_handle(void) { return (void*)ctx().stream; }
+
+int b200_last_error(void) { return ctx().last_error; }
+
+unsigned long long b200_launch_count(void) { return ctx().launches; }
+
+void* b200_malloc(size_t bytes) {
+  void* p = nullptr;
+  if (bytes == 0) bytes = 8;   // keep zero-length vectors addressable
+  if (!B200_CHECK(cudaMalloc(&p, bytes))) return nullptr;
+  return p;
+}
+
+void* b200_calloc(size_t bytes) {
+  void* p = b200_malloc(bytes);
+  if (p) B200_CHECK(cudaMemsetAsync(p, 0, bytes ? bytes : 8, ctx().stream));
+  return p;
+}
+
+void b200_free(void* d_ptr) {
+  if (!d_ptr) return;
+  // cudaFree synchronises the device, so in-flight kernels using d_ptr finish first
+  B200_CHECK(cudaFree(d_ptr));
+}
+
+int b200_ptr_is_device(const void* ptr) {
+  cudaPointerAttributes attr;
+  if (cudaPointerGetAttributes(&attr, ptr) != cudaSuccess) {
+    cudaGetLastError();
+    return 0;
+  }
+  return attr.type == cudaMemoryTypeDevice || attr.type == cudaMemoryTypeManaged;
+}
+
+int b200_copy_in(void* d_dst, const void* src, size_t bytes) {
+  if (bytes == 0) return 0;
+  Context& c = ctx();
+  if (b200_ptr_is_device(src)) {
+    return B200_CHECK(cudaMemcpyAsync(d_dst, src, bytes, cudaMemcpyDeviceToDevice, c.stream)) ? 0 : 1;
+  }
+  // pageable host memory: cudaMemcpyAsync stages it before returning, so the caller may
+  // reuse `src` immediately; ordering with earlier kernels is kept by the stream
+  return B200_CHECK(cudaMemcpyAsync(d_dst, src, bytes, cudaMemcpyHostToDevice, c.stream)) ? 0 : 1;
+}
+
+int b200_copy_out(void* dst, const void* d_src, size_t bytes) {
+  if (bytes == 0) return 0;
+  Context& c = ctx();
+  if (b200_ptr_is_device(dst)) {
+    return B200_CHECK(cudaMemcpyAsync(dst, d_src, bytes, cudaMemcpyDeviceToDevice, c.stream)) ? 0 : 1;
+  }
+  bool ok = B200_CHECK(cudaMemcpyAsync(dst, d_src, bytes, cudaMemcpyDeviceToHost, c.stream));
+  ok &= B200_CHECK(cudaStreamSynchronize(c.stream));
+  return ok ? 0 : 1;
+}
+
+}  // extern "C"

@@ -1,0 +1,278 @@
+// csr.cu -- device CSR matrices: creation, row-block schedule, SpMV and row-wise kernels.
+//
+// Replaces, from the reference CUDA backend: `csr` + cusparseSpMV
+// (algebra/cuda/src/cuda_lin_alg.cu:1053-1063), mat_{l,r}mult_diag kernels (:360-401),
+// thrust reduce_by_key row reductions (:465-498, :1065-1085) and vector_init_abs.  The
+// numerical contract is the CPU backend's (algebra/_common/csc_math.c:114-258).
+#include "csr.cuh"
+
+#include <vector>
+#include <cstring>
+
+using namespace b200;
+
+// ------------------------------------------------------------------- schedule
+int b200_build_schedule(b200_csr* M, const int* rp) {
+  std::vector<int4> desc;
+  std::vector<int4> longs;
+  const int nrows = M->nrows;
+  int r = 0;
+  while (r < nrows) {
+    const int len = rp[r + 1] - rp[r];
+    if (len > kTile) {
+      // long row: chunk it
+      const int nchunks = (len + kTile - 1) / kTile;
+      const int lr      = (int)longs.size();
+      longs.push_back(make_int4(r, (int)desc.size(), nchunks, 0));
+      for (int c = 0; c < nchunks; c++) {
+        const int s = rp[r] + c * kTile;
+        const int e = (s + kTile < rp[r + 1]) ? s + kTile : rp[r + 1];
+        desc.push_back(make_int4(r, -(lr + 1), s, e - s));
+      }
+      r++;
+      continue;
+    }
+    int r1 = r, cnt = 0;
+    while (r1 < nrows && (r1 - r) < kMaxRows) {
+      const int l = rp[r1 + 1] - rp[r1];
+      if (l > kTile || cnt + l > kTile) break;
+      cnt += l;
+      r1++;
+    }
+    const int nr = r1 - r;
+    // group size: smallest power of two >= mean row length, in [1, 32]
+    int lg = 0;
+    const int mean = (cnt + nr - 1) / (nr > 0 ? nr : 1);
+    while ((1 << lg) < mean && lg < 5) lg++;
+    desc.push_back(make_int4(r, nr | (lg << 24), rp[r], cnt));
+    r = r1;
+  }
+  M->nblocks = (int)desc.size();
+  M->nlong   = (int)longs.size();
+  Context& c = ctx();
+  bool ok = true;
+  ok &= B200_CHECK(cudaMalloc(&M->d_desc, sizeof(int4) * (desc.size() + 1)));
+  ok &= B200_CHECK(cudaMalloc(&M->d_long, sizeof(int4) * (longs.size() + 1)));
+  ok &= B200_CHECK(cudaMalloc(&M->d_long_partials, sizeof(double) * (desc.size() + 1)));
+  ok &= B200_CHECK(cudaMalloc(&M->d_long_counters, sizeof(unsigned) * (longs.size() + 1)));
+  if (!ok) return 1;
+  if (!desc.empty())
+    ok &= B200_CHECK(cudaMemcpyAsync(M->d_desc, desc.data(), sizeof(int4) * desc.size(),
+                                     cudaMemcpyHostToDevice, c.stream));
+  if (!longs.empty())
+    ok &= B200_CHECK(cudaMemcpyAsync(M->d_long, longs.data(), sizeof(int4) * longs.size(),
+                                     cudaMemcpyHostToDevice, c.stream));
+  ok &= B200_CHECK(cudaMemsetAsync(M->d_long_counters, 0, sizeof(unsigned) * (longs.size() + 1), c.stream));
+  // desc/longs are pageable host vectors: make sure the copies are done before they die
+  ok &= B200_CHECK(cudaStreamSynchronize(c.stream));
+  return ok ? 0 : 1;
+}
+
+// --------------------------------------------------------------------- kernels
+namespace {
+
+constexpr int kSmElems = kTile + 40;
+
+// y = alpha * M x + beta * y ; one CTA per row block.
+__global__ void __launch_bounds__(kBlock) spmv_kernel(CsrView M, const T* __restrict__ x, T* y,
+                                                      T alpha, T beta) {
+  __shared__ T sm[kSmElems];
+  for (int b = blockIdx.x; b < M.nblocks; b += gridDim.x) {
+    rowblock_apply<SumOp>(
+        M, b, sm, [&](int, int c, T v) { return v * __ldg(x + c); },
+        [&](int row, T s) { y[row] = (beta == (T)0) ? alpha * s : alpha * s + beta * y[row]; });
+  }
+}
+
+__global__ void __launch_bounds__(kBlock) row_absmax_kernel(CsrView M, T* out) {
+  __shared__ T sm[kSmElems];
+  for (int b = blockIdx.x; b < M.nblocks; b += gridDim.x) {
+    rowblock_apply<MaxOp>(
+        M, b, sm, [&](int, int, T v) { return v < (T)0 ? -v : v; },
+        [&](int row, T s) { out[row] = s; });
+  }
+}
+
+__global__ void __launch_bounds__(kBlock) row_wsumsq_kernel(CsrView M, const T* __restrict__ w,
+                                                            T wsc, T* out) {
+  __shared__ T sm[kSmElems];
+  for (int b = blockIdx.x; b < M.nblocks; b += gridDim.x) {
+    rowblock_apply<SumOp>(
+        M, b, sm, [&](int, int c, T v) { return v * v * (w ? __ldg(w + c) : wsc); },
+        [&](int row, T s) { out[row] = s; });
+  }
+}
+
+__global__ void __launch_bounds__(kBlock) diag_kernel(CsrView M, T* out) {
+  __shared__ T sm[kSmElems];
+  for (int b = blockIdx.x; b < M.nblocks; b += gridDim.x) {
+    const int4 d = M.desc[b];
+    const int row_fixed = d.x;
+    const bool is_long = d.y < 0;
+    const int* rp = M.row_ptr;
+    // term = value if the entry sits on the diagonal; the row of entry k is found from the
+    // block descriptor (long chunk: fixed row; normal: binary search in the block's rows)
+    const int nrows = is_long ? 1 : (d.y & 0xffffff);
+    rowblock_apply<SumOp>(
+        M, b, sm,
+        [&](int k, int c, T v) {
+          int row = row_fixed;
+          if (!is_long) {
+            int lo = 0, hi = nrows - 1;
+            while (lo < hi) {
+              int mid = (lo + hi + 1) >> 1;
+              if (__ldg(rp + row_fixed + mid) <= k) lo = mid; else hi = mid - 1;
+            }
+            row = row_fixed + lo;
+          }
+          return (c == row) ? v : (T)0;
+        },
+        [&](int row, T s) { out[row] = s; });
+  }
+}
+
+// val[k] *= L[row(k)] : groups of lanes walk the rows of a block, long chunks use all lanes
+__global__ void __launch_bounds__(kBlock) scale_rows_kernel(CsrView M, const T* __restrict__ L) {
+  for (int b = blockIdx.x; b < M.nblocks; b += gridDim.x) {
+    const int4 d = M.desc[b];
+    if (d.y < 0) {
+      const T s = L[d.x];
+      for (int k = threadIdx.x; k < d.w; k += kBlock) M.val[d.z + k] *= s;
+    } else {
+      const int nrows = d.y & 0xffffff, lg = d.y >> 24, g = 1 << lg;
+      const int gid = threadIdx.x >> lg, lig = threadIdx.x & (g - 1), ngroup = kBlock >> lg;
+      for (int r = gid; r < nrows; r += ngroup) {
+        const T s = L[d.x + r];
+        const int e = M.row_ptr[d.x + r + 1];
+        for (int k = M.row_ptr[d.x + r] + lig; k < e; k += g) M.val[k] *= s;
+      }
+    }
+  }
+}
+
+template <class F>
+__global__ void __launch_bounds__(kBlock) nnz_kernel(int nnz, F f) {
+  const int stride = gridDim.x * blockDim.x;
+  for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < nnz; k += stride) f(k);
+}
+
+inline int rb_grid(const b200_csr* M) {
+  int cap = ctx().sm_count * 8;
+  return M->nblocks < cap ? (M->nblocks > 0 ? M->nblocks : 1) : cap;
+}
+
+}  // namespace
+
+extern "C" {
+
+b200_csr* b200_csr_create(int nrows, int ncols, int nnz, const int* h_row_ptr, const int* h_col_ind,
+                          const T* h_val) {
+  Context& c = ctx();
+  b200_csr* M = new b200_csr();
+  M->nrows = nrows; M->ncols = ncols; M->nnz = nnz;
+  bool ok = true;
+  ok &= B200_CHECK(cudaMalloc(&M->d_row_ptr, sizeof(int) * ((size_t)nrows + 1)));
+  ok &= B200_CHECK(cudaMalloc(&M->d_col_ind, sizeof(int) * ((size_t)nnz + 1)));
+  ok &= B200_CHECK(cudaMalloc(&M->d_val, sizeof(T) * ((size_t)nnz + 1)));
+  if (!ok) { b200_csr_destroy(M); return nullptr; }
+  ok &= B200_CHECK(cudaMemcpyAsync(M->d_row_ptr, h_row_ptr, sizeof(int) * ((size_t)nrows + 1),
+                                   cudaMemcpyHostToDevice, c.stream));
+  if (nnz > 0) {
+    ok &= B200_CHECK(cudaMemcpyAsync(M->d_col_ind, h_col_ind, sizeof(int) * (size_t)nnz,
+                                     cudaMemcpyHostToDevice, c.stream));
+    ok &= B200_CHECK(cudaMemcpyAsync(M->d_val, h_val, sizeof(T) * (size_t)nnz,
+                                     cudaMemcpyHostToDevice, c.stream));
+  }
+  if (!ok || b200_build_schedule(M, h_row_ptr) != 0) { b200_csr_destroy(M); return nullptr; }
+  return M;
+}
+
+void b200_csr_destroy(b200_csr* M) {
+  if (!M) return;
+  cudaFree(M->d_row_ptr);
+  cudaFree(M->d_col_ind);
+  cudaFree(M->d_val);
+  cudaFree(M->d_desc);
+  cudaFree(M->d_long);
+  cudaFree(M->d_long_partials);
+  cudaFree(M->d_long_counters);
+  delete M;
+}
+
+int b200_csr_nrows(const b200_csr* M) { return M->nrows; }
+int b200_csr_ncols(const b200_csr* M) { return M->ncols; }
+int b200_csr_nnz(const b200_csr* M) { return M->nnz; }
+T*  b200_csr_values(b200_csr* M) { return M->d_val; }
+
+int b200_csr_download(const b200_csr* M, int* h_row_ptr, int* h_col_ind, T* h_val) {
+  Context& c = ctx();
+  bool ok = true;
+  if (h_row_ptr)
+    ok &= B200_CHECK(cudaMemcpyAsync(h_row_ptr, M->d_row_ptr, sizeof(int) * ((size_t)M->nrows + 1),
+                                     cudaMemcpyDeviceToHost, c.stream));
+  if (h_col_ind && M->nnz)
+    ok &= B200_CHECK(cudaMemcpyAsync(h_col_ind, M->d_col_ind, sizeof(int) * (size_t)M->nnz,
+                                     cudaMemcpyDeviceToHost, c.stream));
+  if (h_val && M->nnz)
+    ok &= B200_CHECK(cudaMemcpyAsync(h_val, M->d_val, sizeof(T) * (size_t)M->nnz,
+                                     cudaMemcpyDeviceToHost, c.stream));
+  ok &= B200_CHECK(cudaStreamSynchronize(c.stream));
+  return ok ? 0 : 1;
+}
+
+// OSQPMatrix_Axpy / Atxpy core (csc_math.c:169-258); beta == 0 overwrites y.
+void b200_csr_spmv(const b200_csr* M, const T* d_x, T* d_y, T alpha, T beta) {
+  if (M->nrows <= 0) return;
+  spmv_kernel<<<rb_grid(M), kBlock, 0, ctx().stream>>>(M->view(), d_x, d_y, alpha, beta);
+  count_launch();
+}
+
+void b200_csr_scale(b200_csr* M, T sc) {
+  if (M->nnz <= 0) return;
+  T* val = M->d_val;
+  nnz_kernel<<<ew_grid(M->nnz), kBlock, 0, ctx().stream>>>(M->nnz, [=] __device__(int k) { val[k] *= sc; });
+  count_launch();
+}
+
+void b200_csr_scale_rows(b200_csr* M, const T* d_L) {
+  if (M->nnz <= 0) return;
+  scale_rows_kernel<<<rb_grid(M), kBlock, 0, ctx().stream>>>(M->view(), d_L);
+  count_launch();
+}
+
+void b200_csr_scale_cols(b200_csr* M, const T* d_R) {
+  if (M->nnz <= 0) return;
+  T* val = M->d_val;
+  const int* col = M->d_col_ind;
+  nnz_kernel<<<ew_grid(M->nnz), kBlock, 0, ctx().stream>>>(
+      M->nnz, [=] __device__(int k) { val[k] *= d_R[col[k]]; });
+  count_launch();
+}
+
+void b200_csr_row_absmax(const b200_csr* M, T* d_out) {
+  if (M->nrows <= 0) return;
+  row_absmax_kernel<<<rb_grid(M), kBlock, 0, ctx().stream>>>(M->view(), d_out);
+  count_launch();
+}
+
+void b200_csr_row_wsumsq(const b200_csr* M, const T* d_w, T w_scalar, T* d_out) {
+  if (M->nrows <= 0) return;
+  row_wsumsq_kernel<<<rb_grid(M), kBlock, 0, ctx().stream>>>(M->view(), d_w, w_scalar, d_out);
+  count_launch();
+}
+
+void b200_csr_diag(const b200_csr* M, T* d_out) {
+  if (M->nrows <= 0) return;
+  diag_kernel<<<rb_grid(M), kBlock, 0, ctx().stream>>>(M->view(), d_out);
+  count_launch();
+}
+
+int b200_csr_is_eq(const b200_csr* A, const b200_csr* B, T tol) {
+  if (A->nrows != B->nrows || A->ncols != B->ncols || A->nnz != B->nnz) return 0;
+  if (!b200_veci_is_eq(A->d_row_ptr, B->d_row_ptr, A->nrows + 1)) return 0;
+  if (A->nnz == 0) return 1;
+  if (!b200_veci_is_eq(A->d_col_ind, B->d_col_ind, A->nnz)) return 0;
+  return b200_vec_is_eq(A->d_val, B->d_val, tol, A->nnz);
+}
+
+}  // extern "C"
