@@ -47,6 +47,11 @@ void b200_sync(void);                    /* wait for the library stream         
 void* b200_stream_handle(void);          /* cudaStream_t of the library stream      */
 int  b200_last_error(void);              /* sticky CUDA error code, 0 if none       */
 unsigned long long b200_launch_count(void); /* kernels launched since b200_init      */
+/* CUDA-event timing on the library stream (bench.py / profiling only) */
+void* b200_event_create(void);
+void  b200_event_destroy(void* ev);
+void  b200_event_record(void* ev);
+float b200_event_elapsed_ms(void* ev_start, void* ev_stop);   /* waits for ev_stop */
 
 /* --------------------------------------------------------------------- memory
  * replaces cuda_malloc/cuda_calloc/cuda_free + cuda_vec_copy_{h2d,d2h,d2d}

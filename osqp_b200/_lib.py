@@ -36,7 +36,7 @@ def load_kernels(precision="f64"):
             raise B200LibraryMissing(
                 f"{path} not found: build it with `make {precision}` (or __graft_entry__.build()); "
                 "the B200 backend has no CPU fallback")
-        _cache[key] = C.CDLL(str(path), mode=C.RTLD_GLOBAL)
+        _cache[key] = C.CDLL(str(path), mode=C.RTLD_LOCAL)
     return _cache[key]
 
 

@@ -47,7 +47,12 @@ inline bool check(cudaError_t e, const char* what) {
 
 #define B200_CHECK(expr) ::b200::check((expr), #expr)
 
-inline void count_launch() { ctx().launches++; }
+// called after every kernel launch: counts it and records (sticky) launch-configuration errors
+inline void count_launch() {
+  ctx().launches++;
+  cudaError_t e = cudaPeekAtLastError();
+  if (e != cudaSuccess) check(cudaGetLastError(), "kernel launch");
+}
 
 // grid for a grid-stride elementwise kernel: enough CTAs to fill the machine, 4 elements
 // per thread per trip, capped at 8 resident CTAs per SM.

@@ -15,6 +15,9 @@ Context& ctx() {
 
 using namespace b200;
 
+void b200_csr_configure_kernels();
+void b200_pcg_configure_kernels();
+
 extern "C" {
 
 int b200_init(int device) {
@@ -46,6 +49,8 @@ int b200_init(int device) {
   if (!ok) return 1;
   B200_CHECK(cudaMemsetAsync(c.d_ticket, 0, sizeof(unsigned) * 4, c.stream));
   B200_CHECK(cudaMemsetAsync(c.d_scalar, 0, sizeof(double) * kScalarSlots, c.stream));
+  b200_csr_configure_kernels();
+  b200_pcg_configure_kernels();
   c.last_error = 0;
   c.launches   = 0;
   c.refcount   = 1;
@@ -85,6 +90,22 @@ void* b200_stream_handle(void) { return (void*)ctx().stream; }
 int b200_last_error(void) { return ctx().last_error; }
 
 unsigned long long b200_launch_count(void) { return ctx().launches; }
+
+void* b200_event_create(void) {
+  cudaEvent_t e = nullptr;
+  if (!B200_CHECK(cudaEventCreate(&e))) return nullptr;
+  return (void*)e;
+}
+void b200_event_destroy(void* ev) {
+  if (ev) cudaEventDestroy((cudaEvent_t)ev);
+}
+void b200_event_record(void* ev) { B200_CHECK(cudaEventRecord((cudaEvent_t)ev, ctx().stream)); }
+float b200_event_elapsed_ms(void* a, void* b) {
+  float ms = 0.f;
+  B200_CHECK(cudaEventSynchronize((cudaEvent_t)b));
+  B200_CHECK(cudaEventElapsedTime(&ms, (cudaEvent_t)a, (cudaEvent_t)b));
+  return ms;
+}
 
 void* b200_malloc(size_t bytes) {
   void* p = nullptr;

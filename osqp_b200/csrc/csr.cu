@@ -40,10 +40,11 @@ int b200_build_schedule(b200_csr* M, const int* rp) {
       r1++;
     }
     const int nr = r1 - r;
-    // group size: smallest power of two >= mean row length, in [1, 32]
+    // lanes per row: the largest power of two that still gives every row of the block its own
+    // group in ONE trip (32 / nr), but no more lanes than the mean row length needs
     int lg = 0;
     const int mean = (cnt + nr - 1) / (nr > 0 ? nr : 1);
-    while ((1 << lg) < mean && lg < 5) lg++;
+    while (lg < 5 && (2 << lg) * nr <= 32 && (1 << lg) < mean) lg++;
     desc.push_back(make_int4(r, nr | (lg << 24), rp[r], cnt));
     r = r1;
   }
@@ -71,76 +72,66 @@ int b200_build_schedule(b200_csr* M, const int* rp) {
 // --------------------------------------------------------------------- kernels
 namespace {
 
-constexpr int kSmElems = kTile + 40;
 
-// y = alpha * M x + beta * y ; one CTA per row block.
-__global__ void __launch_bounds__(kBlock) spmv_kernel(CsrView M, const T* __restrict__ x, T* y,
-                                                      T alpha, T beta) {
-  __shared__ T sm[kSmElems];
-  for (int b = blockIdx.x; b < M.nblocks; b += gridDim.x) {
-    rowblock_apply<SumOp>(
-        M, b, sm, [&](int, int c, T v) { return v * __ldg(x + c); },
-        [&](int row, T s) { y[row] = (beta == (T)0) ? alpha * s : alpha * s + beta * y[row]; });
-  }
+// y = alpha * M x + beta * y ; CTAs walk the row blocks through the TMA ring.
+__global__ void __launch_bounds__(kSpmvBlock, 2) spmv_kernel(CsrView M, const T* __restrict__ x, T* y,
+                                                             T alpha, T beta) {
+  extern __shared__ __align__(128) unsigned char dsm[];
+  Pipe P = pipe_init(dsm);
+  spmv_pass<SumOp>(
+      M, blockIdx.x, gridDim.x, P, [&](int, int c, T v) { return v * __ldg(x + c); },
+      [&](int row, T s) { y[row] = (beta == (T)0) ? alpha * s : alpha * s + beta * y[row]; });
 }
 
-__global__ void __launch_bounds__(kBlock) row_absmax_kernel(CsrView M, T* out) {
-  __shared__ T sm[kSmElems];
-  for (int b = blockIdx.x; b < M.nblocks; b += gridDim.x) {
-    rowblock_apply<MaxOp>(
-        M, b, sm, [&](int, int, T v) { return v < (T)0 ? -v : v; },
-        [&](int row, T s) { out[row] = s; });
-  }
+__global__ void __launch_bounds__(kSpmvBlock, 2) row_absmax_kernel(CsrView M, T* out) {
+  extern __shared__ __align__(128) unsigned char dsm[];
+  Pipe P = pipe_init(dsm);
+  spmv_pass<MaxOp>(
+      M, blockIdx.x, gridDim.x, P, [&](int, int, T v) { return v < (T)0 ? -v : v; },
+      [&](int row, T s) { out[row] = s; });
 }
 
-__global__ void __launch_bounds__(kBlock) row_wsumsq_kernel(CsrView M, const T* __restrict__ w,
-                                                            T wsc, T* out) {
-  __shared__ T sm[kSmElems];
-  for (int b = blockIdx.x; b < M.nblocks; b += gridDim.x) {
-    rowblock_apply<SumOp>(
-        M, b, sm, [&](int, int c, T v) { return v * v * (w ? __ldg(w + c) : wsc); },
-        [&](int row, T s) { out[row] = s; });
-  }
+__global__ void __launch_bounds__(kSpmvBlock, 2) row_wsumsq_kernel(CsrView M, const T* __restrict__ w,
+                                                                   T wsc, T* out) {
+  extern __shared__ __align__(128) unsigned char dsm[];
+  Pipe P = pipe_init(dsm);
+  spmv_pass<SumOp>(
+      M, blockIdx.x, gridDim.x, P, [&](int, int c, T v) { return v * v * (w ? __ldg(w + c) : wsc); },
+      [&](int row, T s) { out[row] = s; });
 }
 
-__global__ void __launch_bounds__(kBlock) diag_kernel(CsrView M, T* out) {
-  __shared__ T sm[kSmElems];
-  for (int b = blockIdx.x; b < M.nblocks; b += gridDim.x) {
-    const int4 d = M.desc[b];
-    const int row_fixed = d.x;
-    const bool is_long = d.y < 0;
-    const int* rp = M.row_ptr;
-    // term = value if the entry sits on the diagonal; the row of entry k is found from the
-    // block descriptor (long chunk: fixed row; normal: binary search in the block's rows)
-    const int nrows = is_long ? 1 : (d.y & 0xffffff);
-    rowblock_apply<SumOp>(
-        M, b, sm,
-        [&](int k, int c, T v) {
-          int row = row_fixed;
-          if (!is_long) {
-            int lo = 0, hi = nrows - 1;
-            while (lo < hi) {
-              int mid = (lo + hi + 1) >> 1;
-              if (__ldg(rp + row_fixed + mid) <= k) lo = mid; else hi = mid - 1;
-            }
-            row = row_fixed + lo;
-          }
-          return (c == row) ? v : (T)0;
-        },
-        [&](int row, T s) { out[row] = s; });
-  }
+// out[i] = M_ii (0 where absent): the term of entry k is its value iff it sits on the diagonal;
+// the row of entry k is recovered by binary search in the row pointers.
+__global__ void __launch_bounds__(kSpmvBlock, 2) diag_kernel(CsrView M, T* out) {
+  extern __shared__ __align__(128) unsigned char dsm[];
+  Pipe P = pipe_init(dsm);
+  const int* rp = M.row_ptr;
+  const int nrows = M.nrows;
+  spmv_pass<SumOp>(
+      M, blockIdx.x, gridDim.x, P,
+      [&](int k, int c, T v) {
+        int lo = 0, hi = nrows - 1;
+        while (lo < hi) {
+          const int mid = (lo + hi + 1) >> 1;
+          if (__ldg(rp + mid) <= k) lo = mid; else hi = mid - 1;
+        }
+        return (c == lo) ? v : (T)0;
+      },
+      [&](int row, T s) { out[row] = s; });
 }
 
-// val[k] *= L[row(k)] : groups of lanes walk the rows of a block, long chunks use all lanes
-__global__ void __launch_bounds__(kBlock) scale_rows_kernel(CsrView M, const T* __restrict__ L) {
-  for (int b = blockIdx.x; b < M.nblocks; b += gridDim.x) {
-    const int4 d = M.desc[b];
+// val[k] *= L[row(k)] : one warp per tile, groups of lanes walk the rows of the tile
+__global__ void __launch_bounds__(kSpmvBlock) scale_rows_kernel(CsrView M, const T* __restrict__ L) {
+  const int lane = threadIdx.x & 31;
+  const int GW = gridDim.x * kSpmvWarps;
+  for (int t = blockIdx.x * kSpmvWarps + (threadIdx.x >> 5); t < M.nblocks; t += GW) {
+    const int4 d = M.desc[t];
     if (d.y < 0) {
       const T s = L[d.x];
-      for (int k = threadIdx.x; k < d.w; k += kBlock) M.val[d.z + k] *= s;
+      for (int k = lane; k < d.w; k += 32) M.val[d.z + k] *= s;
     } else {
       const int nrows = d.y & 0xffffff, lg = d.y >> 24, g = 1 << lg;
-      const int gid = threadIdx.x >> lg, lig = threadIdx.x & (g - 1), ngroup = kBlock >> lg;
+      const int gid = lane >> lg, lig = lane & (g - 1), ngroup = 32 >> lg;
       for (int r = gid; r < nrows; r += ngroup) {
         const T s = L[d.x + r];
         const int e = M.row_ptr[d.x + r + 1];
@@ -156,12 +147,30 @@ __global__ void __launch_bounds__(kBlock) nnz_kernel(int nnz, F f) {
   for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < nnz; k += stride) f(k);
 }
 
+// persistent-style grid for the pipelined kernels: 2 CTAs (16 warps, ~107 KB smem each) per SM,
+// one tile per warp at a time
 inline int rb_grid(const b200_csr* M) {
-  int cap = ctx().sm_count * 8;
-  return M->nblocks < cap ? (M->nblocks > 0 ? M->nblocks : 1) : cap;
+  int cap  = ctx().sm_count * 2;
+  int want = (M->nblocks + kSpmvWarps - 1) / kSpmvWarps;
+  if (want < 1) want = 1;
+  return want < cap ? want : cap;
+}
+
+template <class K, class... Args>
+inline void launch_spmv(K kernel, const b200_csr* M, Args... args) {
+  kernel<<<rb_grid(M), kSpmvBlock, kSpmvSmemBytes, ctx().stream>>>(M->view(), args...);
+  count_launch();
 }
 
 }  // namespace
+
+// opt every pipelined kernel of this file into > 48 KB dynamic shared memory (called by b200_init)
+void b200_csr_configure_kernels() {
+  b200_enable_spmv_smem(spmv_kernel);
+  b200_enable_spmv_smem(row_absmax_kernel);
+  b200_enable_spmv_smem(row_wsumsq_kernel);
+  b200_enable_spmv_smem(diag_kernel);
+}
 
 extern "C" {
 
@@ -171,9 +180,10 @@ b200_csr* b200_csr_create(int nrows, int ncols, int nnz, const int* h_row_ptr, c
   b200_csr* M = new b200_csr();
   M->nrows = nrows; M->ncols = ncols; M->nnz = nnz;
   bool ok = true;
-  ok &= B200_CHECK(cudaMalloc(&M->d_row_ptr, sizeof(int) * ((size_t)nrows + 1)));
-  ok &= B200_CHECK(cudaMalloc(&M->d_col_ind, sizeof(int) * ((size_t)nnz + 1)));
-  ok &= B200_CHECK(cudaMalloc(&M->d_val, sizeof(T) * ((size_t)nnz + 1)));
+  ok &= B200_CHECK(cudaMalloc(&M->d_row_ptr, sizeof(int) * ((size_t)nrows + 2 * kPad)));
+  // kPad slack: the TMA copies start 16-byte aligned-down and end 16-byte rounded-up
+  ok &= B200_CHECK(cudaMalloc(&M->d_col_ind, sizeof(int) * ((size_t)nnz + 2 * kPad)));
+  ok &= B200_CHECK(cudaMalloc(&M->d_val, sizeof(T) * ((size_t)nnz + 2 * kPad)));
   if (!ok) { b200_csr_destroy(M); return nullptr; }
   ok &= B200_CHECK(cudaMemcpyAsync(M->d_row_ptr, h_row_ptr, sizeof(int) * ((size_t)nrows + 1),
                                    cudaMemcpyHostToDevice, c.stream));
@@ -223,8 +233,7 @@ int b200_csr_download(const b200_csr* M, int* h_row_ptr, int* h_col_ind, T* h_va
 // OSQPMatrix_Axpy / Atxpy core (csc_math.c:169-258); beta == 0 overwrites y.
 void b200_csr_spmv(const b200_csr* M, const T* d_x, T* d_y, T alpha, T beta) {
   if (M->nrows <= 0) return;
-  spmv_kernel<<<rb_grid(M), kBlock, 0, ctx().stream>>>(M->view(), d_x, d_y, alpha, beta);
-  count_launch();
+  launch_spmv(spmv_kernel, M, d_x, d_y, alpha, beta);
 }
 
 void b200_csr_scale(b200_csr* M, T sc) {
@@ -236,7 +245,7 @@ void b200_csr_scale(b200_csr* M, T sc) {
 
 void b200_csr_scale_rows(b200_csr* M, const T* d_L) {
   if (M->nnz <= 0) return;
-  scale_rows_kernel<<<rb_grid(M), kBlock, 0, ctx().stream>>>(M->view(), d_L);
+  scale_rows_kernel<<<rb_grid(M), kSpmvBlock, 0, ctx().stream>>>(M->view(), d_L);
   count_launch();
 }
 
@@ -251,20 +260,17 @@ void b200_csr_scale_cols(b200_csr* M, const T* d_R) {
 
 void b200_csr_row_absmax(const b200_csr* M, T* d_out) {
   if (M->nrows <= 0) return;
-  row_absmax_kernel<<<rb_grid(M), kBlock, 0, ctx().stream>>>(M->view(), d_out);
-  count_launch();
+  launch_spmv(row_absmax_kernel, M, d_out);
 }
 
 void b200_csr_row_wsumsq(const b200_csr* M, const T* d_w, T w_scalar, T* d_out) {
   if (M->nrows <= 0) return;
-  row_wsumsq_kernel<<<rb_grid(M), kBlock, 0, ctx().stream>>>(M->view(), d_w, w_scalar, d_out);
-  count_launch();
+  launch_spmv(row_wsumsq_kernel, M, d_w, w_scalar, d_out);
 }
 
 void b200_csr_diag(const b200_csr* M, T* d_out) {
   if (M->nrows <= 0) return;
-  diag_kernel<<<rb_grid(M), kBlock, 0, ctx().stream>>>(M->view(), d_out);
-  count_launch();
+  launch_spmv(diag_kernel, M, d_out);
 }
 
 int b200_csr_is_eq(const b200_csr* A, const b200_csr* B, T tol) {

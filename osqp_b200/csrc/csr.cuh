@@ -1,14 +1,20 @@
-// csr.cuh -- device CSR view, row-block schedule and the "CSR-stream" row-block primitive
-// shared by the stand-alone SpMV kernel (csr.cu) and the persistent PCG kernel (pcg.cu).
+// csr.cuh -- device CSR view, tile schedule and the TMA-fed warp-centric "CSR-stream" pass shared
+// by the stand-alone SpMV kernels (csr.cu) and the persistent PCG kernel (pcg.cu).
 //
 // Schedule (built once on the host in b200_csr_create):
-//   * a normal block covers whole consecutive rows with <= kTile nonzeros and <= kMaxRows
-//     rows; one CTA streams val/col of the block with fully coalesced loads, stages the
-//     per-entry terms in shared memory, then sub-warp groups of g lanes (g = 1..32, chosen
-//     from the mean row length of the block) reduce one row each with shuffles.
-//   * a row with more than kTile nonzeros is cut into kTile-sized chunks, one CTA each; each
-//     chunk CTA publishes a partial, and the LAST CTA to arrive (atomic ticket on an integer
-//     counter) folds the partials in chunk order -> deterministic, no floating-point atomics.
+//   * a normal tile covers whole consecutive rows with <= kTile nonzeros and <= kMaxRows rows;
+//   * a row with more than kTile nonzeros is cut into kTile-sized chunks, one tile each; each
+//     chunk publishes a partial and the LAST warp to arrive (atomic ticket on an integer counter)
+//     folds the partials in chunk order -> deterministic, no floating-point atomics.
+//
+// Execution (spmv_pass): every WARP owns a private kStages-deep shared-memory ring and walks its
+// tiles t = gw, gw+GW, ... (gw = global warp id) with no CTA-wide barrier at all.  One elected
+// lane issues, per tile, three 1-D TMA bulk copies (cp.async.bulk.shared.global + mbarrier
+// complete_tx): the tile's column indices, values and row pointers, kStages-1 tiles ahead of the
+// arithmetic.  When the tile has landed, the 32 lanes take its entries round-robin (4 independent
+// gathers of the vector in flight per lane), stage the products in shared memory, and groups of
+// g lanes (g = 1..32 from the descriptor) then sum one row each and call the epilogue.
+//
 // Algorithmic bytes of one pass over an r x c matrix with nnz entries:
 //   nnz (sizeof(T)+4) + (r+1) 4 + c sizeof(T) [gather, once] + r sizeof(T) [store]
 // (SURVEY.md section 8d).
@@ -18,8 +24,23 @@
 
 namespace b200 {
 
-constexpr int kTile    = 2048;   // staged nonzeros per CTA pass (16 KB of doubles)
-constexpr int kMaxRows = 1024;   // rows per normal block
+constexpr int kSpmvBlock = 512;    // threads per CTA of every kernel that runs spmv_pass
+constexpr int kSpmvWarps = kSpmvBlock / 32;
+constexpr int kTile      = 128;    // nonzeros per warp tile / stage
+constexpr int kMaxRows   = 64;     // rows per normal tile
+constexpr int kStages    = 3;      // depth of each warp's TMA ring
+constexpr int kPad       = 8;      // slack elements: aligned-down starts + 16-byte rounding
+
+constexpr int kColsBytes  = (kTile + kPad) * 4;
+constexpr int kValsBytes  = (kTile + kPad) * (int)sizeof(T);
+constexpr int kRpBytes    = (kMaxRows + kPad) * 4;
+constexpr int kStageBytes = kColsBytes + kValsBytes + kRpBytes;
+constexpr int kProdBytes  = kTile * (int)sizeof(T);
+constexpr int kWarpBytes  = kStages * kStageBytes + kProdBytes + 32;   // + mbarriers (8 B each)
+constexpr int kSpmvSmemBytes = kSpmvWarps * kWarpBytes;
+static_assert(kColsBytes % 16 == 0 && kValsBytes % 16 == 0 && kRpBytes % 16 == 0 &&
+              kProdBytes % 16 == 0 && kWarpBytes % 16 == 0, "TMA alignment");
+static_assert(kStages * 8 <= 32, "mbarrier slots");
 
 struct CsrView {
   const int*  row_ptr;
@@ -64,75 +85,181 @@ __device__ __forceinline__ T block_reduce_T(T v, T* sh /* >= 33 */) {
   return sh[32];
 }
 
-// Process row block `b` of matrix M.
-//   ef(k, col, val) -> T   term contributed by stored entry k
-//   CB                     combine op over the terms of one row (SumOp / MaxOp)
-//   ep(row, value)         called exactly once per row of the block, by one thread
-// `sm` is CTA shared memory with at least kTile + 40 elements of T.
-template <class CB, class EF, class EP>
-__device__ __forceinline__ void rowblock_apply(const CsrView& M, int b, T* sm, EF ef, EP ep) {
-  const int4 d   = M.desc[b];
-  const int nnz0 = d.z, cnt = d.w;
-  const int tid  = threadIdx.x;
+// ------------------------------------------------------------------ TMA / mbarrier PTX
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  const uint32_t addr = smem_u32(bar);
+  uint32_t done;
+  do {
+    asm volatile(
+        "{\n.reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n}"
+        : "=r"(done)
+        : "r"(addr), "r"(parity)
+        : "memory");
+  } while (!done);
+}
+// 1-D bulk copy global -> shared, completion counted in bytes on `bar`.
+// dst, src 16-byte aligned; bytes a multiple of 16.
+__device__ __forceinline__ void tma_load_1d(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+          smem_u32(dst)),
+      "l"(src), "r"(bytes), "r"(smem_u32(bar))
+      : "memory");
+}
 
-  if (d.y >= 0) {
-    // ---- normal block: stage terms, then per-row group reduction
-    const int nrows = d.y & 0xffffff;
-    const int lg    = d.y >> 24;
-    const int g     = 1 << lg;
-#pragma unroll 4
-    for (int k = tid; k < cnt; k += kBlock) {
-      const int kk = nnz0 + k;
-      sm[k] = ef(kk, __ldg(M.col_ind + kk), M.val[kk]);
-    }
-    __syncthreads();
-    const int gid    = tid >> lg;
-    const int lig    = tid & (g - 1);
-    const int ngroup = kBlock >> lg;
-    for (int base = 0; base < nrows; base += ngroup) {
-      const int r = base + gid;
-      T acc = CB::identity();
-      if (r < nrows) {
-        const int s = __ldg(M.row_ptr + d.x + r) - nnz0;
-        const int e = __ldg(M.row_ptr + d.x + r + 1) - nnz0;
-        for (int k = s + lig; k < e; k += g) acc = CB::apply(acc, sm[k]);
+// Per-warp shared-memory ring.  `it` counts tiles consumed by this warp since pipe_init: tile
+// number `it` lives in stage it % kStages and is the (it / kStages)-th use of that stage's barrier.
+struct Pipe {
+  unsigned char* base;      // this warp's region
+  uint64_t*      bars;
+  T*             prod;      // kTile staged products
+  unsigned       it;
+};
+
+__device__ __forceinline__ Pipe pipe_init(unsigned char* dsm) {
+  Pipe P;
+  const int w = threadIdx.x >> 5;
+  P.base = dsm + w * kWarpBytes;
+  P.prod = reinterpret_cast<T*>(P.base + kStages * kStageBytes);
+  P.bars = reinterpret_cast<uint64_t*>(P.base + kStages * kStageBytes + kProdBytes);
+  P.it   = 0;
+  if ((threadIdx.x & 31) == 0) {
+    for (int s = 0; s < kStages; s++) mbar_init(&P.bars[s], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  return P;
+}
+
+constexpr int kValAlign = 16 / (int)sizeof(T);   // elements of T per 16 bytes
+
+// elected lane: start the three bulk copies of tile t into stage s of this warp's ring
+__device__ __forceinline__ void issue_tile(const CsrView& M, int t, const Pipe& P, int s) {
+  const int4 d = __ldg(M.desc + t);
+  unsigned char* st = P.base + s * kStageBytes;
+  uint64_t* bar = &P.bars[s];
+  const int nnz0 = d.z, cnt = d.w;
+  uint32_t bc = 0, bv = 0, br = 0;
+  const int c0 = nnz0 & ~3, v0 = nnz0 & ~(kValAlign - 1), r0 = d.x & ~3;
+  if (cnt > 0) {
+    bc = (uint32_t)(((nnz0 - c0 + cnt) * 4 + 15) & ~15);
+    bv = (uint32_t)(((nnz0 - v0 + cnt) * (int)sizeof(T) + 15) & ~15);
+  }
+  if (d.y >= 0) br = (uint32_t)(((d.x - r0 + (d.y & 0xffffff) + 1) * 4 + 15) & ~15);
+  mbar_expect_tx(bar, bc + bv + br);
+  if (bc) {
+    tma_load_1d(st, M.col_ind + c0, bc, bar);
+    tma_load_1d(st + kColsBytes, M.val + v0, bv, bar);
+  }
+  if (br) tma_load_1d(st + kColsBytes + kValsBytes, M.row_ptr + r0, br, bar);
+}
+
+// One pass over the tiles of M; the warps of the whole grid take tiles round-robin.
+//   ef(k, col, val) -> T   term contributed by stored entry k (k = global entry index)
+//   CB                     combine op over the terms of one row (SumOp / MaxOp)
+//   ep(row, value)         called exactly once per row, by one thread
+// M.val / M.col_ind / M.row_ptr must not be written while the calling kernel runs (they are read
+// through the async proxy).  All 32 lanes of a warp call this together; warps are independent.
+template <class CB, class EF, class EP>
+__device__ __forceinline__ void spmv_pass(const CsrView& M, int cta, int G, Pipe& P, EF ef, EP ep) {
+  const int lane  = threadIdx.x & 31;
+  const int gw    = cta * kSpmvWarps + (threadIdx.x >> 5);
+  const int GW    = G * kSpmvWarps;
+  const int nmine = (gw < M.nblocks) ? (M.nblocks - gw + GW - 1) / GW : 0;
+  if (lane == 0) {
+    const int pre = nmine < kStages - 1 ? nmine : kStages - 1;
+    for (int i = 0; i < pre; i++) issue_tile(M, gw + i * GW, P, (P.it + i) % kStages);
+  }
+  for (int i = 0; i < nmine; i++) {
+    const int t = gw + i * GW;
+    const int s = P.it % kStages;
+    if (lane == 0 && i + kStages - 1 < nmine)
+      issue_tile(M, t + (kStages - 1) * GW, P, (P.it + kStages - 1) % kStages);
+    const int4 d = __ldg(M.desc + t);
+    const int nnz0 = d.z, cnt = d.w;
+    unsigned char* st = P.base + s * kStageBytes;
+    const int* cols = reinterpret_cast<const int*>(st) + (nnz0 & 3);
+    const T*   vals = reinterpret_cast<const T*>(st + kColsBytes) + (nnz0 & (kValAlign - 1));
+    const int* rp   = reinterpret_cast<const int*>(st + kColsBytes + kValsBytes) + (d.x & 3);
+    mbar_wait(&P.bars[s], (P.it / kStages) & 1);
+
+    if (d.y >= 0) {
+      // ---- normal tile: products by all lanes, then g lanes per row
+      T pr[kTile / 32];
+#pragma unroll
+      for (int u = 0; u < kTile / 32; u++) {
+        const int k = lane + 32 * u;
+        if (k < cnt) pr[u] = ef(nnz0 + k, cols[k], vals[k]);
       }
-      acc = group_reduce<CB>(acc, g);
-      if (r < nrows && lig == 0) ep(d.x + r, acc);
-    }
-    __syncthreads();   // sm is reused by the next block
-  } else {
-    // ---- chunk of a long row
-    const int  lr   = -d.y - 1;
-    const int4 info = M.long_rows[lr];
-    T acc = CB::identity();
-#pragma unroll 4
-    for (int k = tid; k < cnt; k += kBlock) {
-      const int kk = nnz0 + k;
-      acc = CB::apply(acc, ef(kk, __ldg(M.col_ind + kk), M.val[kk]));
-    }
-    T* sh = sm + kTile;
-    acc = block_reduce_T<CB>(acc, sh);
-    __shared__ int s_last;
-    if (tid == 0) {
-      M.long_partials[b] = (double)acc;
-      __threadfence();
-      unsigned t = atomicAdd(&M.long_counters[lr], 1u);
-      s_last = (t == (unsigned)(info.z - 1));
-    }
-    __syncthreads();
-    if (s_last) {
-      __threadfence();
-      T a = CB::identity();
-      for (int c = tid; c < info.z; c += kBlock)
-        a = CB::apply(a, (T)__ldcg(&M.long_partials[info.y + c]));
-      a = block_reduce_T<CB>(a, sh);
-      if (tid == 0) {
-        M.long_counters[lr] = 0;
-        ep(info.x, a);
+#pragma unroll
+      for (int u = 0; u < kTile / 32; u++) {
+        const int k = lane + 32 * u;
+        if (k < cnt) P.prod[k] = pr[u];
+      }
+      __syncwarp();
+      const int nrows  = d.y & 0xffffff;
+      const int lg     = d.y >> 24;
+      const int g      = 1 << lg;
+      const int gid    = lane >> lg;
+      const int lig    = lane & (g - 1);
+      const int ngroup = 32 >> lg;
+      for (int base = 0; base < nrows; base += ngroup) {
+        const int r = base + gid;
+        T acc = CB::identity();
+        if (r < nrows) {
+          const int e = rp[r + 1] - nnz0;
+          for (int k = rp[r] - nnz0 + lig; k < e; k += g) acc = CB::apply(acc, P.prod[k]);
+        }
+        acc = group_reduce<CB>(acc, g);
+        if (r < nrows && lig == 0) ep(d.x + r, acc);
+      }
+    } else {
+      // ---- chunk of a long row: all lanes stride over the chunk
+      const int  lr   = -d.y - 1;
+      const int4 info = __ldg(M.long_rows + lr);
+      T pr[kTile / 32];
+#pragma unroll
+      for (int u = 0; u < kTile / 32; u++) {
+        const int k = lane + 32 * u;
+        pr[u] = (k < cnt) ? ef(nnz0 + k, cols[k], vals[k]) : CB::identity();
+      }
+      T acc = pr[0];
+#pragma unroll
+      for (int u = 1; u < kTile / 32; u++) acc = CB::apply(acc, pr[u]);
+      acc = group_reduce<CB>(acc, 32);
+      int last = 0;
+      if (lane == 0) {
+        M.long_partials[t] = (double)acc;
+        __threadfence();
+        const unsigned tk = atomicAdd(&M.long_counters[lr], 1u);
+        last = (tk == (unsigned)(info.z - 1));
+      }
+      last = __shfl_sync(0xffffffffu, last, 0);
+      if (last) {
+        __threadfence();
+        T a = CB::identity();
+        for (int c = lane; c < info.z; c += 32) a = CB::apply(a, (T)__ldcg(&M.long_partials[info.y + c]));
+        a = group_reduce<CB>(a, 32);
+        if (lane == 0) {
+          M.long_counters[lr] = 0;
+          ep(info.x, a);
+        }
       }
     }
-    __syncthreads();
+    __syncwarp();   // the whole warp is done with stage s (and prod) before they are refilled
+    P.it++;
   }
 }
 
@@ -159,3 +286,9 @@ struct b200_csr {
 
 // build the row-block schedule for a host CSR pattern (shared by csr.cu and pcg.cu)
 int b200_build_schedule(b200_csr* M, const int* h_row_ptr);
+
+// every kernel using spmv_pass needs kSpmvSmemBytes of dynamic shared memory
+template <class K>
+inline void b200_enable_spmv_smem(K kernel) {
+  cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, b200::kSpmvSmemBytes);
+}

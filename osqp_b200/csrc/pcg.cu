@@ -40,7 +40,6 @@ using namespace b200;
 
 namespace {
 
-constexpr int kSmElems = kTile + 40;
 constexpr double kCgTolMin    = 1e-7;   // OSQP_CG_TOL_MIN    (osqp_api_constants.h:215)
 constexpr double kCgPolishTol = 1e-5;   // OSQP_CG_POLISH_TOL (osqp_api_constants.h:216)
 
@@ -72,23 +71,24 @@ struct PcgArgs {
 
 __device__ __forceinline__ double grid_sum(const double* slot, int G, double* shr) {
   double a = 0.0;
-  for (int i = threadIdx.x; i < G; i += kBlock) a += __ldcg(slot + i);
+  for (int i = threadIdx.x; i < G; i += kSpmvBlock) a += __ldcg(slot + i);
   return block_sum(a, shr);
 }
 __device__ __forceinline__ double grid_max(const double* slot, int G, double* shr) {
   double a = 0.0;
-  for (int i = threadIdx.x; i < G; i += kBlock) a = fmax(a, __ldcg(slot + i));
+  for (int i = threadIdx.x; i < G; i += kSpmvBlock) a = fmax(a, __ldcg(slot + i));
   return block_max(a, shr);
 }
 
-__global__ void __launch_bounds__(kBlock, 4) pcg_kernel(PcgArgs a) {
+__global__ void __launch_bounds__(kSpmvBlock, 2) pcg_kernel(PcgArgs a) {
   cg::grid_group grid = cg::this_grid();
-  __shared__ T sm[kSmElems];
+  extern __shared__ __align__(128) unsigned char dsm[];
   __shared__ double shr[33];
+  Pipe pipe = pipe_init(dsm);
 
   const int G = gridDim.x, cta = blockIdx.x, tid = threadIdx.x;
   const int n = a.n, m = a.m;
-  const int gtid = cta * kBlock + tid, gstride = G * kBlock;
+  const int gtid = cta * kSpmvBlock + tid, gstride = G * kSpmvBlock;
   T* const b1 = a.b;
   T* const b2 = a.b + n;
   T* const x = a.x; T* const p = a.p; T* const Kp = a.Kp; T* const r = a.r; T* const t = a.t;
@@ -109,9 +109,8 @@ __global__ void __launch_bounds__(kBlock, 4) pcg_kernel(PcgArgs a) {
     }
     double mx = 0.0;
     if (m > 0) {
-      for (int b = cta; b < a.At.nblocks; b += G)
-        rowblock_apply<SumOp>(
-            a.At, b, sm, [&](int, int c, T v) { return v * t[c]; },
+      spmv_pass<SumOp>(
+          a.At, cta, G, pipe, [&](int, int c, T v) { return v * t[c]; },
             [&](int row, T s) { mx = fmax(mx, fabs((double)(b1[row] + s))); });
     } else {
       for (int i = gtid; i < n; i += gstride) mx = fmax(mx, fabs((double)b1[i]));
@@ -139,18 +138,16 @@ __global__ void __launch_bounds__(kBlock, 4) pcg_kernel(PcgArgs a) {
 
   // ------------------------------------------------------------- P1: t = rho.*(A x - b2)
   if (m > 0) {
-    for (int b = cta; b < a.A.nblocks; b += G)
-      rowblock_apply<SumOp>(
-          a.A, b, sm, [&](int, int c, T v) { return v * x[c]; },
+    spmv_pass<SumOp>(
+          a.A, cta, G, pipe, [&](int, int c, T v) { return v * x[c]; },
           [&](int row, T s) { t[row] = (rho_vec ? rho_vec[row] : rho) * (s - b2[row]); });
     grid.sync();
   }
 
   // ------------------------------------------------------------- P2: initial residual
   double acc_rty = 0.0, acc_max = 0.0;
-  for (int b = cta; b < a.K2.nblocks; b += G)
-    rowblock_apply<SumOp>(
-        a.K2, b, sm, [&](int, int c, T v) { return v * (c < n ? x[c] : t[c - n]); },
+  spmv_pass<SumOp>(
+          a.K2, cta, G, pipe, [&](int, int c, T v) { return v * (c < n ? x[c] : t[c - n]); },
         [&](int row, T s) {
           const T rr = s - b1[row];
           const T yy = minv[row] * rr;
@@ -174,17 +171,15 @@ __global__ void __launch_bounds__(kBlock, 4) pcg_kernel(PcgArgs a) {
   while (rnorm > eps && it < a.max_iter) {
     // L1: t = rho .* (A p)
     if (m > 0) {
-      for (int b = cta; b < a.A.nblocks; b += G)
-        rowblock_apply<SumOp>(
-            a.A, b, sm, [&](int, int c, T v) { return v * p[c]; },
+      spmv_pass<SumOp>(
+          a.A, cta, G, pipe, [&](int, int c, T v) { return v * p[c]; },
             [&](int row, T s) { t[row] = (rho_vec ? rho_vec[row] : rho) * s; });
       grid.sync();
     }
     // L2: Kp = [P + sigma I | A'] [p; t], partial p'Kp
     double acc = 0.0;
-    for (int b = cta; b < a.K2.nblocks; b += G)
-      rowblock_apply<SumOp>(
-          a.K2, b, sm, [&](int, int c, T v) { return v * (c < n ? p[c] : t[c - n]); },
+    spmv_pass<SumOp>(
+          a.K2, cta, G, pipe, [&](int, int c, T v) { return v * (c < n ? p[c] : t[c - n]); },
           [&](int row, T s) {
             Kp[row] = s;
             acc += (double)p[row] * (double)s;
@@ -227,9 +222,8 @@ __global__ void __launch_bounds__(kBlock, 4) pcg_kernel(PcgArgs a) {
   for (int i = gtid; i < n; i += gstride) b1[i] = x[i];
   if (m > 0) {
     const bool pol = a.polishing != 0;
-    for (int b = cta; b < a.A.nblocks; b += G)
-      rowblock_apply<SumOp>(
-          a.A, b, sm, [&](int, int c, T v) { return v * x[c]; },
+    spmv_pass<SumOp>(
+          a.A, cta, G, pipe, [&](int, int c, T v) { return v * x[c]; },
           [&](int row, T s) { b2[row] = pol ? rho * (s - b2[row]) : s; });
   }
   if (cta == 0 && tid == 0) {
@@ -285,6 +279,8 @@ __global__ void precond_kernel(int n, T sigma, const T* pd, const T* ad, T* minv
 
 }  // namespace
 
+void b200_pcg_configure_kernels() { b200_enable_spmv_smem(pcg_kernel); }
+
 struct b200_pcg {
   const b200_csr* P  = nullptr;
   const b200_csr* A  = nullptr;
@@ -326,9 +322,9 @@ b200_pcg* b200_pcg_create(const b200_csr* P, const b200_csr* A, const b200_csr* 
   for (int i = 0; i <= n; i++) rp[i] = rpP[i] + rpAt[i];
   b200_csr& K = s->K2;
   K.nrows = n; K.ncols = n + m; K.nnz = rp[n];
-  ok &= B200_CHECK(cudaMalloc(&K.d_row_ptr, sizeof(int) * ((size_t)n + 1)));
-  ok &= B200_CHECK(cudaMalloc(&K.d_col_ind, sizeof(int) * ((size_t)K.nnz + 1)));
-  ok &= B200_CHECK(cudaMalloc(&K.d_val, sizeof(T) * ((size_t)K.nnz + 1)));
+  ok &= B200_CHECK(cudaMalloc(&K.d_row_ptr, sizeof(int) * ((size_t)n + 2 * kPad)));
+  ok &= B200_CHECK(cudaMalloc(&K.d_col_ind, sizeof(int) * ((size_t)K.nnz + 2 * kPad)));
+  ok &= B200_CHECK(cudaMalloc(&K.d_val, sizeof(T) * ((size_t)K.nnz + 2 * kPad)));
   if (!ok) { b200_pcg_destroy(s); return nullptr; }
   ok &= B200_CHECK(cudaMemcpyAsync(K.d_row_ptr, rp.data(), sizeof(int) * (n + 1), cudaMemcpyHostToDevice, c.stream));
   ok &= B200_CHECK(cudaStreamSynchronize(c.stream));
@@ -336,12 +332,13 @@ b200_pcg* b200_pcg_create(const b200_csr* P, const b200_csr* A, const b200_csr* 
 
   // cooperative grid: all CTAs must be co-resident
   int per_sm = 0;
-  ok &= B200_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pcg_kernel, kBlock, 0));
+  ok &= B200_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pcg_kernel, kSpmvBlock,
+                                                                 kSpmvSmemBytes));
   if (per_sm < 1) per_sm = 1;
   s->max_grid = per_sm * c.sm_count;
-  long long want = K.nblocks;
-  if (A && A->nblocks > want) want = A->nblocks;
-  long long ew = ((long long)n + kBlock * 2 - 1) / (kBlock * 2);
+  long long want = (K.nblocks + kSpmvWarps - 1) / kSpmvWarps;
+  if (A && (A->nblocks + kSpmvWarps - 1) / kSpmvWarps > want) want = (A->nblocks + kSpmvWarps - 1) / kSpmvWarps;
+  long long ew = ((long long)n + kSpmvBlock * 2 - 1) / (kSpmvBlock * 2);
   if (ew > want) want = ew;
   if (want < 1) want = 1;
   s->grid = (int)(want < s->max_grid ? want : s->max_grid);
@@ -411,8 +408,8 @@ int b200_pcg_solve(b200_pcg* s, T* d_b, int admm_iter, double prim_res, double d
   a.prim_res = prim_res; a.dual_res = dual_res; a.tol_fraction = tol_fraction;
   a.st = s->d_state; a.red = s->d_red;
   void* args[] = {&a};
-  bool ok = B200_CHECK(cudaLaunchCooperativeKernel((const void*)pcg_kernel, dim3(s->grid), dim3(kBlock),
-                                                   args, 0, ctx().stream));
+  bool ok = B200_CHECK(cudaLaunchCooperativeKernel((const void*)pcg_kernel, dim3(s->grid), dim3(kSpmvBlock),
+                                                   args, kSpmvSmemBytes, ctx().stream));
   count_launch();
   return ok ? 0 : 1;
 }

@@ -21,6 +21,8 @@ def kernels(precision="f64"):
         "b200_device_name": (i, [C.c_char_p, i]), "b200_sm_count": (i, []),
         "b200_last_error": (i, []), "b200_launch_count": (C.c_ulonglong, []),
         "b200_stream_handle": (vp, []),
+        "b200_event_create": (vp, []), "b200_event_destroy": (None, [vp]),
+        "b200_event_record": (None, [vp]), "b200_event_elapsed_ms": (C.c_float, [vp, vp]),
         "b200_malloc": (vp, [sz]), "b200_calloc": (vp, [sz]), "b200_free": (None, [vp]),
         "b200_copy_in": (i, [vp, vp, sz]), "b200_copy_out": (i, [vp, vp, sz]),
         "b200_ptr_is_device": (i, [vp]),

@@ -32,7 +32,7 @@ class LoadedLibrary:
         self.path = str(path)
         self.dtype = np.dtype(dtype)
         self.T = _capi.TYPES_F64 if self.dtype == np.float64 else _capi.TYPES_F32
-        self.lib = _capi.bind_public_api(C.CDLL(self.path, mode=C.RTLD_GLOBAL), self.T)
+        self.lib = _capi.bind_public_api(C.CDLL(self.path, mode=C.RTLD_LOCAL), self.T)
 
 
 def _csc_struct(T, M, dtype, keep):

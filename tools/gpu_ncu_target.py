@@ -1,0 +1,27 @@
+"""Short workload for ncu captures: a few SpMV launches on the Lasso matrices and a few PCG launches."""
+import sys
+import numpy as np, scipy.sparse as sp
+sys.path.insert(0, ".")
+from osqp_b200 import problems
+from osqp_b200.devmem import kernels, DeviceArray, csr_to_device
+scale = float(sys.argv[1]) if len(sys.argv) > 1 else 1.0
+k = kernels(); assert k.b200_init(0) == 0
+pb = problems.lasso(int(1e5 * scale), int(1e6 * scale))
+A = pb["A"].tocsr(); At = pb["A"].T.tocsr(); n = A.shape[1]; m = A.shape[0]
+rng = np.random.default_rng(0)
+hA, hAt = csr_to_device(k, A), csr_to_device(k, At)
+x = DeviceArray(k, rng.standard_normal(n)); y = DeviceArray(k, n=m); z = DeviceArray(k, rng.standard_normal(m)); w = DeviceArray(k, n=n)
+for _ in range(4):
+    k.b200_csr_spmv(hA, x.ptr, y.ptr, 1.0, 0.0)
+    k.b200_csr_spmv(hAt, z.ptr, w.ptr, 1.0, 0.0)
+Pfull = (sp.csr_matrix(sp.triu(pb["P"]) + sp.triu(pb["P"], 1).T) + sp.eye(n, format="csr") * 1e-300).tocsr()
+hP = csr_to_device(k, Pfull)
+pcg = k.b200_pcg_create(hP, hA, hAt, n, m)
+k.b200_pcg_configure(pcg, 1e-6, 0.1, None, 1, 0)
+k.b200_pcg_refresh_matrices(pcg); k.b200_pcg_refresh_precond(pcg)
+b0 = rng.standard_normal(n + m); bvec = DeviceArray(k, b0); zeros = DeviceArray(k, np.zeros(n))
+for rep in range(3):
+    k.b200_copy_in(bvec.ptr, b0.ctypes.data, b0.nbytes); k.b200_pcg_warm_start(pcg, zeros.ptr)
+    k.b200_pcg_solve(pcg, bvec.ptr, 2, 0.0, 0.0, 4, 0.15, 10)
+k.b200_sync()
+print("done", k.b200_last_error())
