@@ -41,10 +41,10 @@ int b200_build_schedule(b200_csr* M, const int* rp) {
     }
     const int nr = r1 - r;
     // lanes per row: the largest power of two that still gives every row of the block its own
-    // group in ONE trip (32 / nr), but no more lanes than the mean row length needs
+    // group in ONE trip (kSpmvBlock / nr), but no more lanes than the mean row length needs
     int lg = 0;
     const int mean = (cnt + nr - 1) / (nr > 0 ? nr : 1);
-    while (lg < 5 && (2 << lg) * nr <= 32 && (1 << lg) < mean) lg++;
+    while (lg < 5 && (2 << lg) * nr <= kSpmvBlock && (1 << lg) < mean) lg++;
     desc.push_back(make_int4(r, nr | (lg << 24), rp[r], cnt));
     r = r1;
   }
@@ -120,18 +120,16 @@ __global__ void __launch_bounds__(kSpmvBlock, 2) diag_kernel(CsrView M, T* out) 
       [&](int row, T s) { out[row] = s; });
 }
 
-// val[k] *= L[row(k)] : one warp per tile, groups of lanes walk the rows of the tile
+// val[k] *= L[row(k)] : groups of lanes walk the rows of a block, long chunks use all lanes
 __global__ void __launch_bounds__(kSpmvBlock) scale_rows_kernel(CsrView M, const T* __restrict__ L) {
-  const int lane = threadIdx.x & 31;
-  const int GW = gridDim.x * kSpmvWarps;
-  for (int t = blockIdx.x * kSpmvWarps + (threadIdx.x >> 5); t < M.nblocks; t += GW) {
-    const int4 d = M.desc[t];
+  for (int b = blockIdx.x; b < M.nblocks; b += gridDim.x) {
+    const int4 d = M.desc[b];
     if (d.y < 0) {
       const T s = L[d.x];
-      for (int k = lane; k < d.w; k += 32) M.val[d.z + k] *= s;
+      for (int k = threadIdx.x; k < d.w; k += kSpmvBlock) M.val[d.z + k] *= s;
     } else {
       const int nrows = d.y & 0xffffff, lg = d.y >> 24, g = 1 << lg;
-      const int gid = lane >> lg, lig = lane & (g - 1), ngroup = 32 >> lg;
+      const int gid = threadIdx.x >> lg, lig = threadIdx.x & (g - 1), ngroup = kSpmvBlock >> lg;
       for (int r = gid; r < nrows; r += ngroup) {
         const T s = L[d.x + r];
         const int e = M.row_ptr[d.x + r + 1];
@@ -147,13 +145,10 @@ __global__ void __launch_bounds__(kBlock) nnz_kernel(int nnz, F f) {
   for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < nnz; k += stride) f(k);
 }
 
-// persistent-style grid for the pipelined kernels: 2 CTAs (16 warps, ~107 KB smem each) per SM,
-// one tile per warp at a time
+// persistent-style grid for the pipelined kernels: 2 CTAs (512 threads, ~103 KB smem) per SM
 inline int rb_grid(const b200_csr* M) {
-  int cap  = ctx().sm_count * 2;
-  int want = (M->nblocks + kSpmvWarps - 1) / kSpmvWarps;
-  if (want < 1) want = 1;
-  return want < cap ? want : cap;
+  int cap = ctx().sm_count * 2;
+  return M->nblocks < cap ? (M->nblocks > 0 ? M->nblocks : 1) : cap;
 }
 
 template <class K, class... Args>
@@ -245,7 +240,7 @@ void b200_csr_scale(b200_csr* M, T sc) {
 
 void b200_csr_scale_rows(b200_csr* M, const T* d_L) {
   if (M->nnz <= 0) return;
-  scale_rows_kernel<<<rb_grid(M), kSpmvBlock, 0, ctx().stream>>>(M->view(), d_L);
+  scale_rows_kernel<<<rb_grid(M) * 2, kSpmvBlock, 0, ctx().stream>>>(M->view(), d_L);
   count_launch();
 }
 

@@ -1,19 +1,22 @@
-// csr.cuh -- device CSR view, tile schedule and the TMA-fed warp-centric "CSR-stream" pass shared
-// by the stand-alone SpMV kernels (csr.cu) and the persistent PCG kernel (pcg.cu).
+// csr.cuh -- device CSR view, row-block schedule and the TMA-fed "CSR-stream" pass shared by the
+// stand-alone SpMV kernels (csr.cu) and the persistent PCG kernel (pcg.cu).
 //
 // Schedule (built once on the host in b200_csr_create):
-//   * a normal tile covers whole consecutive rows with <= kTile nonzeros and <= kMaxRows rows;
-//   * a row with more than kTile nonzeros is cut into kTile-sized chunks, one tile each; each
-//     chunk publishes a partial and the LAST warp to arrive (atomic ticket on an integer counter)
+//   * a normal block covers whole consecutive rows with <= kTile nonzeros and <= kMaxRows rows;
+//   * a row with more than kTile nonzeros is cut into kTile-sized chunks, one block each; each
+//     chunk publishes a partial and the LAST CTA to arrive (atomic ticket on an integer counter)
 //     folds the partials in chunk order -> deterministic, no floating-point atomics.
 //
-// Execution (spmv_pass): every WARP owns a private kStages-deep shared-memory ring and walks its
-// tiles t = gw, gw+GW, ... (gw = global warp id) with no CTA-wide barrier at all.  One elected
-// lane issues, per tile, three 1-D TMA bulk copies (cp.async.bulk.shared.global + mbarrier
-// complete_tx): the tile's column indices, values and row pointers, kStages-1 tiles ahead of the
-// arithmetic.  When the tile has landed, the 32 lanes take its entries round-robin (4 independent
-// gathers of the vector in flight per lane), stage the products in shared memory, and groups of
-// g lanes (g = 1..32 from the descriptor) then sum one row each and call the epilogue.
+// Execution (spmv_pass): a CTA walks its blocks b = cta, cta+G, ... through a kStages-deep
+// shared-memory ring.  One elected thread issues, per block, three 1-D TMA bulk copies
+// (cp.async.bulk.shared.global + mbarrier complete_tx): the block's column indices, values and
+// row pointers, kStages-1 blocks ahead of the arithmetic, so the HBM stream costs no registers,
+// no LSU issue slots and no exposed latency.  When a block has landed, ALL threads take its
+// entries round-robin and issue their gathers of the vector in one dense burst (the gather is
+// the scarce resource: measured 1 divergent 8-byte gather per clock per SM on B200, see
+// tools/micro/gather_bench.cu), stage the products in shared memory, and groups of g lanes
+// (g = 1..32 from the descriptor) then sum one row each and call the epilogue.  Two CTAs per SM
+// alternate so that one gathers while the other reduces.
 //
 // Algorithmic bytes of one pass over an r x c matrix with nnz entries:
 //   nnz (sizeof(T)+4) + (r+1) 4 + c sizeof(T) [gather, once] + r sizeof(T) [store]
@@ -25,22 +28,22 @@
 namespace b200 {
 
 constexpr int kSpmvBlock = 512;    // threads per CTA of every kernel that runs spmv_pass
-constexpr int kSpmvWarps = kSpmvBlock / 32;
-constexpr int kTile      = 128;    // nonzeros per warp tile / stage
-constexpr int kMaxRows   = 64;     // rows per normal tile
-constexpr int kStages    = 3;      // depth of each warp's TMA ring
+constexpr int kTile      = 2048;   // nonzeros per block / stage
+constexpr int kMaxRows   = 1024;   // rows per normal block
+constexpr int kStages    = 3;      // depth of the TMA ring
 constexpr int kPad       = 8;      // slack elements: aligned-down starts + 16-byte rounding
+constexpr int kGU        = kTile / kSpmvBlock;   // gathers in flight per thread
 
 constexpr int kColsBytes  = (kTile + kPad) * 4;
 constexpr int kValsBytes  = (kTile + kPad) * (int)sizeof(T);
 constexpr int kRpBytes    = (kMaxRows + kPad) * 4;
 constexpr int kStageBytes = kColsBytes + kValsBytes + kRpBytes;
 constexpr int kProdBytes  = kTile * (int)sizeof(T);
-constexpr int kWarpBytes  = kStages * kStageBytes + kProdBytes + 32;   // + mbarriers (8 B each)
-constexpr int kSpmvSmemBytes = kSpmvWarps * kWarpBytes;
+constexpr int kScratchElems = 40;
+constexpr int kSpmvSmemBytes = kStages * kStageBytes + kProdBytes +
+                               kScratchElems * (int)sizeof(double) + kStages * 8 + 16;
 static_assert(kColsBytes % 16 == 0 && kValsBytes % 16 == 0 && kRpBytes % 16 == 0 &&
-              kProdBytes % 16 == 0 && kWarpBytes % 16 == 0, "TMA alignment");
-static_assert(kStages * 8 <= 32, "mbarrier slots");
+              kProdBytes % 16 == 0, "TMA alignment");
 
 struct CsrView {
   const int*  row_ptr;
@@ -119,23 +122,27 @@ __device__ __forceinline__ void tma_load_1d(void* dst, const void* src, uint32_t
       : "memory");
 }
 
-// Per-warp shared-memory ring.  `it` counts tiles consumed by this warp since pipe_init: tile
-// number `it` lives in stage it % kStages and is the (it / kStages)-th use of that stage's barrier.
+// Shared-memory ring of one CTA.  `it` counts blocks consumed since pipe_init: block number `it`
+// lives in stage it % kStages and is the (it / kStages)-th use of that stage's barrier.
 struct Pipe {
-  unsigned char* base;      // this warp's region
-  uint64_t*      bars;
+  unsigned char* base;
   T*             prod;      // kTile staged products
+  T*             scratch;   // reduction scratch
+  uint64_t*      bars;
+  int*           flag;      // last-arriver broadcast
   unsigned       it;
 };
 
 __device__ __forceinline__ Pipe pipe_init(unsigned char* dsm) {
   Pipe P;
-  const int w = threadIdx.x >> 5;
-  P.base = dsm + w * kWarpBytes;
-  P.prod = reinterpret_cast<T*>(P.base + kStages * kStageBytes);
-  P.bars = reinterpret_cast<uint64_t*>(P.base + kStages * kStageBytes + kProdBytes);
-  P.it   = 0;
-  if ((threadIdx.x & 31) == 0) {
+  P.base    = dsm;
+  P.prod    = reinterpret_cast<T*>(dsm + kStages * kStageBytes);
+  P.scratch = reinterpret_cast<T*>(dsm + kStages * kStageBytes + kProdBytes);
+  P.bars    = reinterpret_cast<uint64_t*>(dsm + kStages * kStageBytes + kProdBytes +
+                                          kScratchElems * sizeof(double));
+  P.flag    = reinterpret_cast<int*>(P.bars + kStages);
+  P.it      = 0;
+  if (threadIdx.x == 0) {
     for (int s = 0; s < kStages; s++) mbar_init(&P.bars[s], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -145,9 +152,9 @@ __device__ __forceinline__ Pipe pipe_init(unsigned char* dsm) {
 
 constexpr int kValAlign = 16 / (int)sizeof(T);   // elements of T per 16 bytes
 
-// elected lane: start the three bulk copies of tile t into stage s of this warp's ring
-__device__ __forceinline__ void issue_tile(const CsrView& M, int t, const Pipe& P, int s) {
-  const int4 d = __ldg(M.desc + t);
+// elected thread: start the three bulk copies of block b into stage s
+__device__ __forceinline__ void issue_block(const CsrView& M, int b, const Pipe& P, int s) {
+  const int4 d = __ldg(M.desc + b);
   unsigned char* st = P.base + s * kStageBytes;
   uint64_t* bar = &P.bars[s];
   const int nnz0 = d.z, cnt = d.w;
@@ -166,28 +173,27 @@ __device__ __forceinline__ void issue_tile(const CsrView& M, int t, const Pipe& 
   if (br) tma_load_1d(st + kColsBytes + kValsBytes, M.row_ptr + r0, br, bar);
 }
 
-// One pass over the tiles of M; the warps of the whole grid take tiles round-robin.
+// One pass over the blocks cta, cta+G, ... of M.
 //   ef(k, col, val) -> T   term contributed by stored entry k (k = global entry index)
 //   CB                     combine op over the terms of one row (SumOp / MaxOp)
 //   ep(row, value)         called exactly once per row, by one thread
 // M.val / M.col_ind / M.row_ptr must not be written while the calling kernel runs (they are read
-// through the async proxy).  All 32 lanes of a warp call this together; warps are independent.
+// through the async proxy).  All threads of the CTA must call this together.
 template <class CB, class EF, class EP>
 __device__ __forceinline__ void spmv_pass(const CsrView& M, int cta, int G, Pipe& P, EF ef, EP ep) {
-  const int lane  = threadIdx.x & 31;
-  const int gw    = cta * kSpmvWarps + (threadIdx.x >> 5);
-  const int GW    = G * kSpmvWarps;
-  const int nmine = (gw < M.nblocks) ? (M.nblocks - gw + GW - 1) / GW : 0;
-  if (lane == 0) {
+  const int tid   = threadIdx.x;
+  const int nmine = (cta < M.nblocks) ? (M.nblocks - cta + G - 1) / G : 0;
+  if (tid == 0) {
     const int pre = nmine < kStages - 1 ? nmine : kStages - 1;
-    for (int i = 0; i < pre; i++) issue_tile(M, gw + i * GW, P, (P.it + i) % kStages);
+    for (int i = 0; i < pre; i++) issue_block(M, cta + i * G, P, (P.it + i) % kStages);
   }
+  T* const prod = P.prod;
   for (int i = 0; i < nmine; i++) {
-    const int t = gw + i * GW;
+    const int b = cta + i * G;
     const int s = P.it % kStages;
-    if (lane == 0 && i + kStages - 1 < nmine)
-      issue_tile(M, t + (kStages - 1) * GW, P, (P.it + kStages - 1) % kStages);
-    const int4 d = __ldg(M.desc + t);
+    if (tid == 0 && i + kStages - 1 < nmine)
+      issue_block(M, b + (kStages - 1) * G, P, (P.it + kStages - 1) % kStages);
+    const int4 d = __ldg(M.desc + b);
     const int nnz0 = d.z, cnt = d.w;
     unsigned char* st = P.base + s * kStageBytes;
     const int* cols = reinterpret_cast<const int*>(st) + (nnz0 & 3);
@@ -195,70 +201,72 @@ __device__ __forceinline__ void spmv_pass(const CsrView& M, int cta, int G, Pipe
     const int* rp   = reinterpret_cast<const int*>(st + kColsBytes + kValsBytes) + (d.x & 3);
     mbar_wait(&P.bars[s], (P.it / kStages) & 1);
 
+    // ---- dense gather burst: kGU independent gathers per thread
+    T pr[kGU];
+#pragma unroll
+    for (int u = 0; u < kGU; u++) {
+      const int k = tid + u * kSpmvBlock;
+      pr[u] = (k < cnt) ? ef(nnz0 + k, cols[k], vals[k]) : CB::identity();
+    }
+
     if (d.y >= 0) {
-      // ---- normal tile: products by all lanes, then g lanes per row
-      T pr[kTile / 32];
+      // ---- normal block: stage products, then g lanes per row
 #pragma unroll
-      for (int u = 0; u < kTile / 32; u++) {
-        const int k = lane + 32 * u;
-        if (k < cnt) pr[u] = ef(nnz0 + k, cols[k], vals[k]);
+      for (int u = 0; u < kGU; u++) {
+        const int k = tid + u * kSpmvBlock;
+        if (k < cnt) prod[k] = pr[u];
       }
-#pragma unroll
-      for (int u = 0; u < kTile / 32; u++) {
-        const int k = lane + 32 * u;
-        if (k < cnt) P.prod[k] = pr[u];
-      }
-      __syncwarp();
+      __syncthreads();
       const int nrows  = d.y & 0xffffff;
       const int lg     = d.y >> 24;
       const int g      = 1 << lg;
-      const int gid    = lane >> lg;
-      const int lig    = lane & (g - 1);
-      const int ngroup = 32 >> lg;
+      const int gid    = tid >> lg;
+      const int lig    = tid & (g - 1);
+      const int ngroup = kSpmvBlock >> lg;
       for (int base = 0; base < nrows; base += ngroup) {
         const int r = base + gid;
         T acc = CB::identity();
         if (r < nrows) {
+          int k = rp[r] - nnz0 + lig;
           const int e = rp[r + 1] - nnz0;
-          for (int k = rp[r] - nnz0 + lig; k < e; k += g) acc = CB::apply(acc, P.prod[k]);
+          for (; k + 3 * g < e; k += 4 * g) {
+            const T t0 = prod[k], t1 = prod[k + g], t2 = prod[k + 2 * g], t3 = prod[k + 3 * g];
+            acc = CB::apply(CB::apply(acc, t0), t1);
+            acc = CB::apply(CB::apply(acc, t2), t3);
+          }
+          for (; k < e; k += g) acc = CB::apply(acc, prod[k]);
         }
         acc = group_reduce<CB>(acc, g);
         if (r < nrows && lig == 0) ep(d.x + r, acc);
       }
     } else {
-      // ---- chunk of a long row: all lanes stride over the chunk
+      // ---- chunk of a long row
       const int  lr   = -d.y - 1;
       const int4 info = __ldg(M.long_rows + lr);
-      T pr[kTile / 32];
-#pragma unroll
-      for (int u = 0; u < kTile / 32; u++) {
-        const int k = lane + 32 * u;
-        pr[u] = (k < cnt) ? ef(nnz0 + k, cols[k], vals[k]) : CB::identity();
-      }
       T acc = pr[0];
 #pragma unroll
-      for (int u = 1; u < kTile / 32; u++) acc = CB::apply(acc, pr[u]);
-      acc = group_reduce<CB>(acc, 32);
-      int last = 0;
-      if (lane == 0) {
-        M.long_partials[t] = (double)acc;
+      for (int u = 1; u < kGU; u++) acc = CB::apply(acc, pr[u]);
+      acc = block_reduce_T<CB>(acc, P.scratch);
+      if (tid == 0) {
+        M.long_partials[b] = (double)acc;
         __threadfence();
-        const unsigned tk = atomicAdd(&M.long_counters[lr], 1u);
-        last = (tk == (unsigned)(info.z - 1));
+        const unsigned t = atomicAdd(&M.long_counters[lr], 1u);
+        *P.flag = (t == (unsigned)(info.z - 1));
       }
-      last = __shfl_sync(0xffffffffu, last, 0);
-      if (last) {
+      __syncthreads();
+      if (*P.flag) {
         __threadfence();
         T a = CB::identity();
-        for (int c = lane; c < info.z; c += 32) a = CB::apply(a, (T)__ldcg(&M.long_partials[info.y + c]));
-        a = group_reduce<CB>(a, 32);
-        if (lane == 0) {
+        for (int c = tid; c < info.z; c += kSpmvBlock)
+          a = CB::apply(a, (T)__ldcg(&M.long_partials[info.y + c]));
+        a = block_reduce_T<CB>(a, P.scratch);
+        if (tid == 0) {
           M.long_counters[lr] = 0;
           ep(info.x, a);
         }
       }
     }
-    __syncwarp();   // the whole warp is done with stage s (and prod) before they are refilled
+    __syncthreads();   // everyone is done with stage s and prod before they are refilled
     P.it++;
   }
 }

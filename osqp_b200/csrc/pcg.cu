@@ -336,8 +336,8 @@ b200_pcg* b200_pcg_create(const b200_csr* P, const b200_csr* A, const b200_csr* 
                                                                  kSpmvSmemBytes));
   if (per_sm < 1) per_sm = 1;
   s->max_grid = per_sm * c.sm_count;
-  long long want = (K.nblocks + kSpmvWarps - 1) / kSpmvWarps;
-  if (A && (A->nblocks + kSpmvWarps - 1) / kSpmvWarps > want) want = (A->nblocks + kSpmvWarps - 1) / kSpmvWarps;
+  long long want = K.nblocks;
+  if (A && A->nblocks > want) want = A->nblocks;
   long long ew = ((long long)n + kSpmvBlock * 2 - 1) / (kSpmvBlock * 2);
   if (ew > want) want = ew;
   if (want < 1) want = 1;

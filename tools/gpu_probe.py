@@ -43,6 +43,16 @@ for name, M in (("A", A), ("At", At)):
     byts = M.nnz * (F + 4) + (M.shape[0] + 1) * 4 + M.shape[1] * F + M.shape[0] * F
     print(f"spmv {name}: {ms*1e3:.1f} us  {byts/ms/1e6:.0f} GB/s  ({byts/1e6:.1f} MB)", flush=True)
     k.b200_csr_destroy(h)
+# banded matrix with the same row lengths as A but consecutive columns: cost of everything
+# except the random gather
+Ab = A.copy(); Ab.sort_indices()
+rl = np.diff(Ab.indptr); starts = (np.arange(m) * 7) % max(1, n - rl.max() - 1)
+Ab.indices = (np.repeat(starts, rl) + (np.arange(Ab.nnz) - np.repeat(Ab.indptr[:-1], rl))).astype(np.int32)
+h = csr_to_device(k, Ab); x = DeviceArray(k, rng.standard_normal(n)); y = DeviceArray(k, n=m)
+ms = time_kernel(lambda: k.b200_csr_spmv(h, x.ptr, y.ptr, 1.0, 0.0))
+byts = Ab.nnz * (F + 4) + (m + 1) * 4 + n * F + m * F
+print(f"spmv banded(A): {ms*1e3:.1f} us  {byts/ms/1e6:.0f} GB/s", flush=True)
+k.b200_csr_destroy(h)
 v1 = DeviceArray(k, rng.standard_normal(n)); v2 = DeviceArray(k, rng.standard_normal(n)); v3 = DeviceArray(k, n=n)
 ms = time_kernel(lambda: k.b200_vec_add_scaled(v3.ptr, 1.0, v1.ptr, 2.0, v2.ptr, n))
 print(f"add_scaled n={n}: {ms*1e3:.1f} us {3*n*F/ms/1e6:.0f} GB/s", flush=True)
