@@ -74,7 +74,7 @@ namespace {
 
 
 // y = alpha * M x + beta * y ; CTAs walk the row blocks through the TMA ring.
-__global__ void __launch_bounds__(kSpmvBlock, 2) spmv_kernel(CsrView M, const T* __restrict__ x, T* y,
+__global__ void __launch_bounds__(kSpmvBlock) spmv_kernel(CsrView M, const T* __restrict__ x, T* y,
                                                              T alpha, T beta) {
   extern __shared__ __align__(128) unsigned char dsm[];
   Pipe P = pipe_init(dsm);
@@ -83,7 +83,7 @@ __global__ void __launch_bounds__(kSpmvBlock, 2) spmv_kernel(CsrView M, const T*
       [&](int row, T s) { y[row] = (beta == (T)0) ? alpha * s : alpha * s + beta * y[row]; });
 }
 
-__global__ void __launch_bounds__(kSpmvBlock, 2) row_absmax_kernel(CsrView M, T* out) {
+__global__ void __launch_bounds__(kSpmvBlock) row_absmax_kernel(CsrView M, T* out) {
   extern __shared__ __align__(128) unsigned char dsm[];
   Pipe P = pipe_init(dsm);
   spmv_pass<MaxOp>(
@@ -91,7 +91,7 @@ __global__ void __launch_bounds__(kSpmvBlock, 2) row_absmax_kernel(CsrView M, T*
       [&](int row, T s) { out[row] = s; });
 }
 
-__global__ void __launch_bounds__(kSpmvBlock, 2) row_wsumsq_kernel(CsrView M, const T* __restrict__ w,
+__global__ void __launch_bounds__(kSpmvBlock) row_wsumsq_kernel(CsrView M, const T* __restrict__ w,
                                                                    T wsc, T* out) {
   extern __shared__ __align__(128) unsigned char dsm[];
   Pipe P = pipe_init(dsm);
@@ -102,7 +102,7 @@ __global__ void __launch_bounds__(kSpmvBlock, 2) row_wsumsq_kernel(CsrView M, co
 
 // out[i] = M_ii (0 where absent): the term of entry k is its value iff it sits on the diagonal;
 // the row of entry k is recovered by binary search in the row pointers.
-__global__ void __launch_bounds__(kSpmvBlock, 2) diag_kernel(CsrView M, T* out) {
+__global__ void __launch_bounds__(kSpmvBlock) diag_kernel(CsrView M, T* out) {
   extern __shared__ __align__(128) unsigned char dsm[];
   Pipe P = pipe_init(dsm);
   const int* rp = M.row_ptr;
@@ -145,9 +145,9 @@ __global__ void __launch_bounds__(kBlock) nnz_kernel(int nnz, F f) {
   for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < nnz; k += stride) f(k);
 }
 
-// persistent-style grid for the pipelined kernels: 2 CTAs (512 threads, ~103 KB smem) per SM
+// one CTA per row block, capped at 8 resident CTAs per SM (grid-stride beyond that)
 inline int rb_grid(const b200_csr* M) {
-  int cap = ctx().sm_count * 2;
+  int cap = ctx().sm_count * 8;
   return M->nblocks < cap ? (M->nblocks > 0 ? M->nblocks : 1) : cap;
 }
 
@@ -240,7 +240,7 @@ void b200_csr_scale(b200_csr* M, T sc) {
 
 void b200_csr_scale_rows(b200_csr* M, const T* d_L) {
   if (M->nnz <= 0) return;
-  scale_rows_kernel<<<rb_grid(M) * 2, kSpmvBlock, 0, ctx().stream>>>(M->view(), d_L);
+  scale_rows_kernel<<<rb_grid(M), kSpmvBlock, 0, ctx().stream>>>(M->view(), d_L);
   count_launch();
 }
 

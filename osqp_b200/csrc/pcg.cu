@@ -80,7 +80,7 @@ __device__ __forceinline__ double grid_max(const double* slot, int G, double* sh
   return block_max(a, shr);
 }
 
-__global__ void __launch_bounds__(kSpmvBlock, 2) pcg_kernel(PcgArgs a) {
+__global__ void __launch_bounds__(kSpmvBlock, 4) pcg_kernel(PcgArgs a) {
   cg::grid_group grid = cg::this_grid();
   extern __shared__ __align__(128) unsigned char dsm[];
   __shared__ double shr[33];
