@@ -284,11 +284,17 @@ void OSQPMatrix_Atxpy(const OSQPMatrix* A, const OSQPVectorf* x, OSQPVectorf* y,
 /* ---------------------------------------------------------------------- norms */
 
 void OSQPMatrix_col_norm_inf(const OSQPMatrix* M, OSQPVectorf* E) {
-  /* columns of A are rows of A'; P is symmetric */
-  b200_csr_row_absmax(M->is_symmetric ? M->S : M->St, E->d_val);
+  /* columns of A are rows of A'.  For P the CPU reference takes the column norms of the stored
+     UPPER TRIANGLE only (algebra/builtin/matrix.c:194-197 -> csc_col_norm_inf on the triu CSC),
+     unlike the reference CUDA backend which uses the full symmetric matrix
+     (algebra/cuda/matrix.cu:136-140).  The builtin backend is the parity oracle, so the Ruiz
+     scaling (scaling.c:38) follows it. */
+  if (M->is_symmetric) b200_csr_row_absmax_lower(M->S, E->d_val);
+  else                 b200_csr_row_absmax(M->St, E->d_val);
 }
 
 void OSQPMatrix_row_norm_inf(const OSQPMatrix* M, OSQPVectorf* E) {
+  /* symmetric: full row norms (csc_row_norm_inf_sym_triu, csc_math.c:335-363) */
   b200_csr_row_absmax(M->S, E->d_val);
 }
 

@@ -139,6 +139,10 @@ void b200_csr_scale(b200_csr* M, b200_float sc);                    /* M *= sc  
 void b200_csr_scale_rows(b200_csr* M, const b200_float* d_L);       /* M = diag(L) M    */
 void b200_csr_scale_cols(b200_csr* M, const b200_float* d_R);       /* M = M diag(R)    */
 void b200_csr_row_absmax(const b200_csr* M, b200_float* d_out);     /* max_j |M_ij|     */
+/* symmetric M stored in full: d_out[j] = max_{i<=j} |M_ij|, i.e. the column norms of the UPPER
+ * TRIANGLE only -- what the CPU reference computes for P (algebra/builtin/matrix.c:194-197 calls
+ * csc_col_norm_inf on the triu CSC; the symmetric variant is only used for row norms) */
+void b200_csr_row_absmax_lower(const b200_csr* M, b200_float* d_out);
 /* d_out[i] = sum_j M_ij^2 * w_j   (w == NULL -> w_j = w_scalar): Jacobi diagonal of A' R A
  * when M = A' (algebra/cuda/lin_sys/indirect/cuda_pcg.cu:236-251) */
 void b200_csr_row_wsumsq(const b200_csr* M, const b200_float* d_w, b200_float w_scalar,

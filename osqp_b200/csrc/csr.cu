@@ -120,6 +120,26 @@ __global__ void __launch_bounds__(kSpmvBlock) diag_kernel(CsrView M, T* out) {
       [&](int row, T s) { out[row] = s; });
 }
 
+// out[j] = max_{i <= j} |M_ij| of a SYMMETRIC matrix stored in full: the column norms of its upper
+// triangle, read row-wise from the mirrored lower triangle (entries with col <= row).
+__global__ void __launch_bounds__(kSpmvBlock) row_absmax_lower_kernel(CsrView M, T* out) {
+  extern __shared__ __align__(128) unsigned char dsm[];
+  Pipe P = pipe_init(dsm);
+  const int* rp = M.row_ptr;
+  const int nrows = M.nrows;
+  spmv_pass<MaxOp>(
+      M, blockIdx.x, gridDim.x, P,
+      [&](int k, int c, T v) {
+        int lo = 0, hi = nrows - 1;
+        while (lo < hi) {
+          const int mid = (lo + hi + 1) >> 1;
+          if (__ldg(rp + mid) <= k) lo = mid; else hi = mid - 1;
+        }
+        return (c <= lo) ? (v < (T)0 ? -v : v) : (T)0;
+      },
+      [&](int row, T s) { out[row] = s; });
+}
+
 // val[k] *= L[row(k)] : groups of lanes walk the rows of a block, long chunks use all lanes
 __global__ void __launch_bounds__(kSpmvBlock) scale_rows_kernel(CsrView M, const T* __restrict__ L) {
   for (int b = blockIdx.x; b < M.nblocks; b += gridDim.x) {
@@ -165,6 +185,7 @@ void b200_csr_configure_kernels() {
   b200_enable_spmv_smem(row_absmax_kernel);
   b200_enable_spmv_smem(row_wsumsq_kernel);
   b200_enable_spmv_smem(diag_kernel);
+  b200_enable_spmv_smem(row_absmax_lower_kernel);
 }
 
 extern "C" {
@@ -256,6 +277,11 @@ void b200_csr_scale_cols(b200_csr* M, const T* d_R) {
 void b200_csr_row_absmax(const b200_csr* M, T* d_out) {
   if (M->nrows <= 0) return;
   launch_spmv(row_absmax_kernel, M, d_out);
+}
+
+void b200_csr_row_absmax_lower(const b200_csr* M, T* d_out) {
+  if (M->nrows <= 0) return;
+  launch_spmv(row_absmax_lower_kernel, M, d_out);
 }
 
 void b200_csr_row_wsumsq(const b200_csr* M, const T* d_w, T w_scalar, T* d_out) {

@@ -110,7 +110,7 @@ void b200_vec_set_scalar_cond(T* a, const int* test, T neg, T zero, T pos, int n
 void b200_vec_round_to_zero(T* a, T tol, int n) {
   launch_ew(n, [=] __device__(int i) {
     T v = a[i];
-    if (v >= -tol && v <= tol) a[i] = (T)0;
+    if ((v < (T)0 ? -v : v) < tol) a[i] = (T)0;   // strict, like algebra/builtin/vector.c:345-356
   });
 }
 

@@ -63,6 +63,7 @@ def kernels(precision="f64"):
         "b200_csr_scale": (None, [vp, F]),
         "b200_csr_scale_rows": (None, [vp, vp]), "b200_csr_scale_cols": (None, [vp, vp]),
         "b200_csr_row_absmax": (None, [vp, vp]),
+        "b200_csr_row_absmax_lower": (None, [vp, vp]),
         "b200_csr_row_wsumsq": (None, [vp, vp, F, vp]),
         "b200_csr_diag": (None, [vp, vp]),
         "b200_csr_is_eq": (i, [vp, vp, F]),
