@@ -32,6 +32,8 @@ def load_kernels(precision="f64"):
     key = ("kernels", precision)
     if key not in _cache:
         path, _ = lib_paths(precision)
+        if os.environ.get("B200_KERNELS_LIB"):       # development: kernel-library variants
+            path = Path(os.environ["B200_KERNELS_LIB"])
         if not path.exists():
             raise B200LibraryMissing(
                 f"{path} not found: build it with `make {precision}` (or __graft_entry__.build()); "

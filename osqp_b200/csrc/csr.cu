@@ -74,7 +74,7 @@ namespace {
 
 
 // y = alpha * M x + beta * y ; CTAs walk the row blocks through the TMA ring.
-__global__ void __launch_bounds__(kSpmvBlock) spmv_kernel(CsrView M, const T* __restrict__ x, T* y,
+__global__ void __launch_bounds__(kSpmvBlock, B200_SPMV_MINBLOCKS) spmv_kernel(CsrView M, const T* __restrict__ x, T* y,
                                                              T alpha, T beta) {
   extern __shared__ __align__(128) unsigned char dsm[];
   Pipe P = pipe_init(dsm);
@@ -83,7 +83,7 @@ __global__ void __launch_bounds__(kSpmvBlock) spmv_kernel(CsrView M, const T* __
       [&](int row, T s) { y[row] = (beta == (T)0) ? alpha * s : alpha * s + beta * y[row]; });
 }
 
-__global__ void __launch_bounds__(kSpmvBlock) row_absmax_kernel(CsrView M, T* out) {
+__global__ void __launch_bounds__(kSpmvBlock, B200_SPMV_MINBLOCKS) row_absmax_kernel(CsrView M, T* out) {
   extern __shared__ __align__(128) unsigned char dsm[];
   Pipe P = pipe_init(dsm);
   spmv_pass<MaxOp>(
@@ -91,7 +91,7 @@ __global__ void __launch_bounds__(kSpmvBlock) row_absmax_kernel(CsrView M, T* ou
       [&](int row, T s) { out[row] = s; });
 }
 
-__global__ void __launch_bounds__(kSpmvBlock) row_wsumsq_kernel(CsrView M, const T* __restrict__ w,
+__global__ void __launch_bounds__(kSpmvBlock, B200_SPMV_MINBLOCKS) row_wsumsq_kernel(CsrView M, const T* __restrict__ w,
                                                                    T wsc, T* out) {
   extern __shared__ __align__(128) unsigned char dsm[];
   Pipe P = pipe_init(dsm);
@@ -102,7 +102,7 @@ __global__ void __launch_bounds__(kSpmvBlock) row_wsumsq_kernel(CsrView M, const
 
 // out[i] = M_ii (0 where absent): the term of entry k is its value iff it sits on the diagonal;
 // the row of entry k is recovered by binary search in the row pointers.
-__global__ void __launch_bounds__(kSpmvBlock) diag_kernel(CsrView M, T* out) {
+__global__ void __launch_bounds__(kSpmvBlock, B200_SPMV_MINBLOCKS) diag_kernel(CsrView M, T* out) {
   extern __shared__ __align__(128) unsigned char dsm[];
   Pipe P = pipe_init(dsm);
   const int* rp = M.row_ptr;
@@ -122,7 +122,7 @@ __global__ void __launch_bounds__(kSpmvBlock) diag_kernel(CsrView M, T* out) {
 
 // out[j] = max_{i <= j} |M_ij| of a SYMMETRIC matrix stored in full: the column norms of its upper
 // triangle, read row-wise from the mirrored lower triangle (entries with col <= row).
-__global__ void __launch_bounds__(kSpmvBlock) row_absmax_lower_kernel(CsrView M, T* out) {
+__global__ void __launch_bounds__(kSpmvBlock, B200_SPMV_MINBLOCKS) row_absmax_lower_kernel(CsrView M, T* out) {
   extern __shared__ __align__(128) unsigned char dsm[];
   Pipe P = pipe_init(dsm);
   const int* rp = M.row_ptr;
@@ -141,7 +141,7 @@ __global__ void __launch_bounds__(kSpmvBlock) row_absmax_lower_kernel(CsrView M,
 }
 
 // val[k] *= L[row(k)] : groups of lanes walk the rows of a block, long chunks use all lanes
-__global__ void __launch_bounds__(kSpmvBlock) scale_rows_kernel(CsrView M, const T* __restrict__ L) {
+__global__ void __launch_bounds__(kSpmvBlock, B200_SPMV_MINBLOCKS) scale_rows_kernel(CsrView M, const T* __restrict__ L) {
   for (int b = blockIdx.x; b < M.nblocks; b += gridDim.x) {
     const int4 d = M.desc[b];
     if (d.y < 0) {

@@ -30,9 +30,21 @@
 
 namespace b200 {
 
-constexpr int kSpmvBlock = 256;    // threads per CTA of every kernel that runs spmv_pass
-constexpr int kTile      = 2048;   // staged nonzeros per CTA pass (16 KB of doubles)
-constexpr int kMaxRows   = 1024;   // rows per normal block
+#ifndef B200_SPMV_BLOCK
+#define B200_SPMV_BLOCK 256
+#endif
+#ifndef B200_SPMV_TILE
+#define B200_SPMV_TILE 2048
+#endif
+#ifndef B200_SPMV_MINBLOCKS
+#define B200_SPMV_MINBLOCKS 1
+#endif
+#ifndef B200_PCG_MINBLOCKS
+#define B200_PCG_MINBLOCKS 4
+#endif
+constexpr int kSpmvBlock = B200_SPMV_BLOCK;  // threads per CTA of every kernel that runs spmv_pass
+constexpr int kTile      = B200_SPMV_TILE;   // staged nonzeros per CTA pass
+constexpr int kMaxRows   = kTile / 2;        // rows per normal block
 constexpr int kPad       = 8;      // slack elements at the end of every matrix array
 
 constexpr int kSmemElems     = kTile + 40;                  // staged terms + reduction scratch
@@ -124,7 +136,11 @@ __device__ __forceinline__ Pipe pipe_init(unsigned char* dsm) {
 template <class CB, class EF, class EP>
 __device__ __forceinline__ void spmv_pass(const CsrView& M, int cta, int G, Pipe& P, EF ef, EP ep) {
   const int tid = threadIdx.x;
-  constexpr int kU = 4;   // independent (col, val, gather) chains in flight per thread
+  // independent (col, val, gather) chains in flight per thread.  Measured on the Lasso matrix
+  // (tools/micro/spmv_variants.cu, profiles/r01_spmv_ncu.md): lean stand-alone kernels prefer one
+  // batch per tile (56 us), the register-bound persistent PCG kernel prefers 2048-entry tiles in
+  // two batches of 4 (204 us / CG iteration vs 212-243 for the other tilings).
+  constexpr int kU = 4;
   T* const sm = P.sm;
   for (int b = cta; b < M.nblocks; b += G) {
     const int4 d   = __ldg(M.desc + b);
@@ -161,14 +177,8 @@ __device__ __forceinline__ void spmv_pass(const CsrView& M, int cta, int G, Pipe
         const int r = base + gid;
         T acc = CB::identity();
         if (r < nrows) {
-          int k = srp[r] + lig;
           const int e = srp[r + 1];
-          for (; k + 3 * g < e; k += 4 * g) {
-            const T t0 = sm[k], t1 = sm[k + g], t2 = sm[k + 2 * g], t3 = sm[k + 3 * g];
-            acc = CB::apply(CB::apply(acc, t0), t1);
-            acc = CB::apply(CB::apply(acc, t2), t3);
-          }
-          for (; k < e; k += g) acc = CB::apply(acc, sm[k]);
+          for (int k = srp[r] + lig; k < e; k += g) acc = CB::apply(acc, sm[k]);
         }
         acc = group_reduce<CB>(acc, g);
         if (r < nrows && lig == 0) ep(d.x + r, acc);

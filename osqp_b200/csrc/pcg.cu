@@ -15,59 +15,38 @@
 //
 // Kernel plan (grid = co-resident CTAs, phases separated by grid.sync()):
 //   [R]  only when admm_iter == 1 or polishing: ||b1 + A'(rho.*b2)||_inf for the tolerance
-//   P1   t = rho .* (A x - b2)                       SpMV over A   (m rows)
+//   P1   t = rho .* (A x - b2)          elementwise from the carried A x (a pass over A only when
+//                                       the carried product is stale: first solve, after warm_start /
+//                                       matrix updates, and every kAxResync solves)
 //   P2   r = [P+sigma I | A'] [x; t] - b1 ; p = -M^-1 r ; partials r'y, ||r||_inf
 //   loop while ||r||_inf > eps and it < max_iter:
-//     L1 t  = rho .* (A p)                           SpMV over A
-//     L2 Kp = [P+sigma I | A'] [p; t] ; partial p'Kp SpMV over the fused operator (n rows)
-//     L3 x += a p ; r += a Kp ; partials r'y, ||r||_inf      (y = M^-1 r stays in registers)
+//     L1 w = A p ; t = rho .* w                       SpMV over A
+//     L2 Kp = [P+sigma I | A'] [p; t] ; partial p'Kp  SpMV over the fused operator (n rows)
+//     L3 x += a p ; r += a Kp ; Ax += a w ; partials r'y, ||r||_inf   (y = M^-1 r in registers)
 //     L4 p  = beta p - M^-1 r
-//   E1   b1 = x ; b2 = A x   (or (A x - b2)/delta when polishing)
+//   E1   b1 = x ; b2 = A x (carried; or (A x - b2)/delta when polishing)
+// Carrying A x through the CG recurrence (A x_{k+1} = A x_k + a A p_k, and A p_k is computed in
+// L1 anyway) removes two of the 2k+3 matrix passes of a solve; the product is recomputed
+// exactly every kAxResync solves so rounding drift stays at the 1e-13 level.
 // Every grid-wide scalar is a fixed-order sum of per-CTA partials -> deterministic for a
 // given grid; no floating-point atomics; zero host synchronisation.
 //
-// Algorithmic HBM bytes per CG iteration (F = sizeof(T)):
-//   L1: nnzA (F+4) + (m+1) 4 + n F + m F            L2: (nnzP + nnzA)(F+4) + (n+1) 4 + (n+m) F + 2 n F
-//   L3: 5 n F read + 2 n F write                    L4: 3 n F read + n F write
-#include "csr.cuh"
+// Algorithmic HBM bytes (F = sizeof(T)), SpMV(r x c, nnz) = nnz (F+4) + (r+1) 4 + c F + r F:
+//   per CG iteration : SpMV(A) + SpMV([P|A']) + 8 n F      (K.p + 8nF)
+//   per launch, fixed: SpMV([P|A']) + (3n + 3m) F          (initial residual + rhs/write-back)
+#include "pcg.cuh"
 
 #include <cooperative_groups.h>
 #include <vector>
 #include <cstring>
+#include <cstdlib>
 
 namespace cg = cooperative_groups;
 using namespace b200;
 
 namespace {
 
-constexpr double kCgTolMin    = 1e-7;   // OSQP_CG_TOL_MIN    (osqp_api_constants.h:215)
-constexpr double kCgPolishTol = 1e-5;   // OSQP_CG_POLISH_TOL (osqp_api_constants.h:216)
 
-enum { SLOT_RHS = 0, SLOT_RTY = 1, SLOT_RMAX = 2, SLOT_PKP = 3, SLOT_COUNT = 4 };
-
-struct PcgState {
-  double    reduction_factor;
-  double    eps_prev;
-  double    last_eps;
-  double    last_rnorm;
-  long long total_iters;
-  long long n_solves;
-  int       zero_iters;
-  int       last_iters;
-};
-
-struct PcgArgs {
-  CsrView K2, A, At;
-  int n, m;
-  T *x, *p, *Kp, *r, *t, *b;
-  const T* minv;
-  const T* rho_vec;
-  T rho;
-  int admm_iter, max_iter, polishing, reduction_threshold;
-  double prim_res, dual_res, tol_fraction;
-  PcgState* st;
-  double* red;   // SLOT_COUNT * gridDim.x
-};
 
 __device__ __forceinline__ double grid_sum(const double* slot, int G, double* shr) {
   double a = 0.0;
@@ -80,7 +59,7 @@ __device__ __forceinline__ double grid_max(const double* slot, int G, double* sh
   return block_max(a, shr);
 }
 
-__global__ void __launch_bounds__(kSpmvBlock, 4) pcg_kernel(PcgArgs a) {
+__global__ void __launch_bounds__(kSpmvBlock, B200_PCG_MINBLOCKS) pcg_kernel(PcgArgs a) {
   cg::grid_group grid = cg::this_grid();
   extern __shared__ __align__(128) unsigned char dsm[];
   __shared__ double shr[33];
@@ -92,6 +71,7 @@ __global__ void __launch_bounds__(kSpmvBlock, 4) pcg_kernel(PcgArgs a) {
   T* const b1 = a.b;
   T* const b2 = a.b + n;
   T* const x = a.x; T* const p = a.p; T* const Kp = a.Kp; T* const r = a.r; T* const t = a.t;
+  T* const Ax = a.Ax; T* const w = a.w;
   const T* const minv = a.minv;
   const T* const rho_vec = a.rho_vec;
   const T rho = a.rho;
@@ -138,9 +118,16 @@ __global__ void __launch_bounds__(kSpmvBlock, 4) pcg_kernel(PcgArgs a) {
 
   // ------------------------------------------------------------- P1: t = rho.*(A x - b2)
   if (m > 0) {
-    spmv_pass<SumOp>(
+    if (a.ax_valid) {
+      for (int j = gtid; j < m; j += gstride) t[j] = (rho_vec ? rho_vec[j] : rho) * (Ax[j] - b2[j]);
+    } else {
+      spmv_pass<SumOp>(
           a.A, cta, G, pipe, [&](int, int c, T v) { return v * x[c]; },
-          [&](int row, T s) { t[row] = (rho_vec ? rho_vec[row] : rho) * (s - b2[row]); });
+          [&](int row, T s) {
+            Ax[row] = s;
+            t[row]  = (rho_vec ? rho_vec[row] : rho) * (s - b2[row]);
+          });
+    }
     grid.sync();
   }
 
@@ -173,7 +160,10 @@ __global__ void __launch_bounds__(kSpmvBlock, 4) pcg_kernel(PcgArgs a) {
     if (m > 0) {
       spmv_pass<SumOp>(
           a.A, cta, G, pipe, [&](int, int c, T v) { return v * p[c]; },
-            [&](int row, T s) { t[row] = (rho_vec ? rho_vec[row] : rho) * s; });
+          [&](int row, T s) {
+            w[row] = s;
+            t[row] = (rho_vec ? rho_vec[row] : rho) * s;
+          });
       grid.sync();
     }
     // L2: Kp = [P + sigma I | A'] [p; t], partial p'Kp
@@ -200,6 +190,7 @@ __global__ void __launch_bounds__(kSpmvBlock, 4) pcg_kernel(PcgArgs a) {
       acc_rty += (double)rr * (double)yy;
       acc_max = fmax(acc_max, fabs((double)rr));
     }
+    for (int j = gtid; j < m; j += gstride) Ax[j] += alpha * w[j];
     acc_rty = block_sum(acc_rty, shr);
     acc_max = block_max(acc_max, shr);
     if (tid == 0) {
@@ -222,9 +213,7 @@ __global__ void __launch_bounds__(kSpmvBlock, 4) pcg_kernel(PcgArgs a) {
   for (int i = gtid; i < n; i += gstride) b1[i] = x[i];
   if (m > 0) {
     const bool pol = a.polishing != 0;
-    spmv_pass<SumOp>(
-          a.A, cta, G, pipe, [&](int, int c, T v) { return v * x[c]; },
-          [&](int row, T s) { b2[row] = pol ? rho * (s - b2[row]) : s; });
+    for (int j = gtid; j < m; j += gstride) b2[j] = pol ? rho * (Ax[j] - b2[j]) : Ax[j];
   }
   if (cta == 0 && tid == 0) {
     PcgState o = st;
@@ -279,23 +268,10 @@ __global__ void precond_kernel(int n, T sigma, const T* pd, const T* ad, T* minv
 
 }  // namespace
 
-void b200_pcg_configure_kernels() { b200_enable_spmv_smem(pcg_kernel); }
-
-struct b200_pcg {
-  const b200_csr* P  = nullptr;
-  const b200_csr* A  = nullptr;
-  const b200_csr* At = nullptr;
-  b200_csr K2;
-  int n = 0, m = 0;
-  T *d_x = nullptr, *d_p = nullptr, *d_Kp = nullptr, *d_r = nullptr, *d_t = nullptr;
-  T *d_minv = nullptr, *d_pd = nullptr, *d_ad = nullptr;
-  const T* d_rho_vec = nullptr;
-  T sigma = 0, rho = 0;
-  int precond = 1, polishing = 0;
-  PcgState* d_state = nullptr;
-  double*   d_red   = nullptr;
-  int grid = 1, max_grid = 1;
-};
+void b200_pcg_configure_kernels() {
+  b200_enable_spmv_smem(pcg_kernel);
+  b200_pcg_graph_configure_kernels();
+}
 
 extern "C" {
 
@@ -307,6 +283,7 @@ b200_pcg* b200_pcg_create(const b200_csr* P, const b200_csr* A, const b200_csr* 
   auto alloc = [&](T** p, size_t cnt) { ok &= B200_CHECK(cudaMalloc(p, sizeof(T) * (cnt + 1))); };
   alloc(&s->d_x, n); alloc(&s->d_p, n); alloc(&s->d_Kp, n); alloc(&s->d_r, n);
   alloc(&s->d_t, m); alloc(&s->d_minv, n); alloc(&s->d_pd, n); alloc(&s->d_ad, n);
+  alloc(&s->d_Ax, m); alloc(&s->d_w, m);
   ok &= B200_CHECK(cudaMalloc(&s->d_state, sizeof(PcgState)));
   if (!ok) { b200_pcg_destroy(s); return nullptr; }
   B200_CHECK(cudaMemsetAsync(s->d_x, 0, sizeof(T) * (n + 1), c.stream));   // PCG iterate starts at 0
@@ -344,13 +321,26 @@ b200_pcg* b200_pcg_create(const b200_csr* P, const b200_csr* A, const b200_csr* 
   s->grid = (int)(want < s->max_grid ? want : s->max_grid);
   ok &= B200_CHECK(cudaMalloc(&s->d_red, sizeof(double) * SLOT_COUNT * s->max_grid));
   if (!ok) { b200_pcg_destroy(s); return nullptr; }
+  // driver choice: the graph driver (lean kernels, WHILE node) pays ~8 launches per solve
+  // (measured round 1: the two drivers are within 5 % of each other on the 1.14e7-nnz Lasso, so the
+  // persistent kernel stays the default; B200_PCG_DRIVER=graph selects the graph driver, which is
+  // also the structure a row-sharded solve needs: kernel boundaries where the all-reduce goes)
+  const char* env = getenv("B200_PCG_DRIVER");
+  s->use_graph = env ? (strcmp(env, "graph") == 0) : 0;
+  if (s->use_graph && b200_pcg_graph_build(s) != 0) {
+    fprintf(stderr, "[osqp_b200] graph PCG driver unavailable, using the persistent kernel\n");
+    b200_pcg_graph_destroy(s);
+    s->use_graph = 0;
+  }
   return s;
 }
 
 void b200_pcg_destroy(b200_pcg* s) {
   if (!s) return;
   cudaFree(s->d_x); cudaFree(s->d_p); cudaFree(s->d_Kp); cudaFree(s->d_r); cudaFree(s->d_t);
+  cudaFree(s->d_Ax); cudaFree(s->d_w);
   cudaFree(s->d_minv); cudaFree(s->d_pd); cudaFree(s->d_ad);
+  b200_pcg_graph_destroy(s);
   cudaFree(s->d_state); cudaFree(s->d_red);
   cudaFree(s->K2.d_row_ptr); cudaFree(s->K2.d_col_ind); cudaFree(s->K2.d_val);
   cudaFree(s->K2.d_desc); cudaFree(s->K2.d_long); cudaFree(s->K2.d_long_partials);
@@ -366,6 +356,7 @@ void b200_pcg_configure(b200_pcg* s, T sigma, T rho, const T* d_rho_vec, int pre
 void b200_pcg_refresh_matrices(b200_pcg* s) {
   Context& c = ctx();
   const int n = s->n;
+  s->ax_valid = 0;   // A may have changed
   if (n <= 0) return;
   const bool hasA = s->m > 0;
   int grid = (n + (kBlock >> 5) - 1) / (kBlock >> 5);
@@ -389,6 +380,7 @@ void b200_pcg_refresh_precond(b200_pcg* s) {
 }
 
 void b200_pcg_warm_start(b200_pcg* s, const T* d_x) {
+  s->ax_valid = 0;   // the iterate is replaced: the carried A x is stale
   if (s->n > 0)
     B200_CHECK(cudaMemcpyAsync(s->d_x, d_x, sizeof(T) * s->n, cudaMemcpyDeviceToDevice, ctx().stream));
 }
@@ -402,11 +394,19 @@ int b200_pcg_solve(b200_pcg* s, T* d_b, int admm_iter, double prim_res, double d
   if (s->m > 0) { a.A = s->A->view(); a.At = s->At->view(); }   // m == 0: no A phases at all
   a.n = s->n; a.m = s->m;
   a.x = s->d_x; a.p = s->d_p; a.Kp = s->d_Kp; a.r = s->d_r; a.t = s->d_t; a.b = d_b;
+  a.Ax = s->d_Ax; a.w = s->d_w;
+  // carried A x: recomputed exactly when stale, when polishing, and every kAxResync solves
+  if (s->polishing || s->solves_since_sync >= kAxResync) s->ax_valid = 0;
+  a.ax_valid = s->ax_valid;
+  if (!s->ax_valid) s->solves_since_sync = 0;
+  s->solves_since_sync++;
+  s->ax_valid = 1;
   a.minv = s->d_minv; a.rho_vec = s->d_rho_vec; a.rho = s->rho;
   a.admm_iter = admm_iter; a.max_iter = max_iter; a.polishing = s->polishing;
   a.reduction_threshold = reduction_threshold;
   a.prim_res = prim_res; a.dual_res = dual_res; a.tol_fraction = tol_fraction;
   a.st = s->d_state; a.red = s->d_red;
+  if (s->use_graph) return b200_pcg_graph_solve(s, a);
   void* args[] = {&a};
   bool ok = B200_CHECK(cudaLaunchCooperativeKernel((const void*)pcg_kernel, dim3(s->grid), dim3(kSpmvBlock),
                                                    args, kSpmvSmemBytes, ctx().stream));

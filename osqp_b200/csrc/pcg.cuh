@@ -1,0 +1,84 @@
+// pcg.cuh -- state shared by the two device-resident PCG drivers:
+//   pcg.cu        one persistent cooperative kernel per solve (grid.sync between phases); lowest
+//                 launch latency, used for small problems
+//   pcg_graph.cu  lean one-CTA-per-tile kernels; the CG loop is a CUDA-graph WHILE node whose
+//                 condition is set on the device, so there is still no host synchronisation;
+//                 higher occupancy per pass, used for large problems
+#pragma once
+
+#include "csr.cuh"
+
+namespace b200 {
+
+constexpr double kCgTolMin    = 1e-7;   // OSQP_CG_TOL_MIN    (osqp_api_constants.h:215)
+constexpr double kCgPolishTol = 1e-5;   // OSQP_CG_POLISH_TOL (osqp_api_constants.h:216)
+constexpr int    kAxResync    = 50;     // solves between exact recomputations of the carried A x
+
+enum { SLOT_RHS = 0, SLOT_RTY = 1, SLOT_RMAX = 2, SLOT_PKP = 3, SLOT_COUNT = 4 };
+
+struct PcgState {
+  double    reduction_factor;
+  double    eps_prev;
+  double    last_eps;
+  double    last_rnorm;
+  long long total_iters;
+  long long n_solves;
+  int       zero_iters;
+  int       last_iters;
+};
+
+struct PcgArgs {
+  CsrView K2, A, At;
+  int n, m;
+  T *x, *p, *Kp, *r, *t, *b, *Ax, *w;
+  const T* minv;
+  const T* rho_vec;
+  T rho;
+  int admm_iter, max_iter, polishing, reduction_threshold, ax_valid;
+  double prim_res, dual_res, tol_fraction;
+  PcgState* st;
+  double* red;   // SLOT_COUNT * gridDim.x
+};
+
+
+// running scalars of one solve in the graph driver (device memory)
+struct PcgRun {
+  double   eps, rTy, rnorm, pKp, beta, rhs_norm;
+  double   rf, eps_prev;
+  int      it, zero_iters;
+  unsigned ticket[SLOT_COUNT];
+};
+
+}  // namespace b200
+
+struct b200_pcg {
+  const b200_csr* P  = nullptr;
+  const b200_csr* A  = nullptr;
+  const b200_csr* At = nullptr;
+  b200_csr K2;
+  int n = 0, m = 0;
+  T *d_x = nullptr, *d_p = nullptr, *d_Kp = nullptr, *d_r = nullptr, *d_t = nullptr;
+  T *d_Ax = nullptr, *d_w = nullptr;
+  int ax_valid = 0, solves_since_sync = 0;
+  T *d_minv = nullptr, *d_pd = nullptr, *d_ad = nullptr;
+  const T* d_rho_vec = nullptr;
+  T sigma = 0, rho = 0;
+  int precond = 1, polishing = 0;
+  b200::PcgState* d_state = nullptr;
+  double*   d_red   = nullptr;
+  int grid = 1, max_grid = 1;
+  // graph driver
+  int use_graph = 0;
+  b200::PcgArgs* d_args = nullptr;
+  b200::PcgRun*  d_run  = nullptr;
+  double*        d_gred = nullptr;     // SLOT_COUNT * gred_stride partials
+  int            gred_stride = 0;
+  void*          graph_exec = nullptr; // cudaGraphExec_t of the CG loop
+  void*          graph      = nullptr;
+};
+
+// pcg_graph.cu
+int  b200_pcg_graph_build(b200_pcg* s);
+void b200_pcg_graph_destroy(b200_pcg* s);
+int  b200_pcg_graph_solve(b200_pcg* s, const b200::PcgArgs& a);
+void b200_pcg_graph_configure_kernels();

@@ -19,9 +19,10 @@ hP = csr_to_device(k, Pfull)
 pcg = k.b200_pcg_create(hP, hA, hAt, n, m)
 k.b200_pcg_configure(pcg, 1e-6, 0.1, None, 1, 0)
 k.b200_pcg_refresh_matrices(pcg); k.b200_pcg_refresh_precond(pcg)
-b0 = rng.standard_normal(n + m); bvec = DeviceArray(k, b0); zeros = DeviceArray(k, np.zeros(n))
-for rep in range(3):
-    k.b200_copy_in(bvec.ptr, b0.ctypes.data, b0.nbytes); k.b200_pcg_warm_start(pcg, zeros.ptr)
-    k.b200_pcg_solve(pcg, bvec.ptr, 2, 0.0, 0.0, 4, 0.15, 10)
+rhs = [DeviceArray(k, rng.standard_normal(n + m)) for _ in range(2)]; bvec = DeviceArray(k, n=n + m)
+KCG = int(sys.argv[2]) if len(sys.argv) > 2 else 3
+for rep in range(4):
+    k.b200_copy_in(bvec.ptr, rhs[rep % 2].ptr, (n + m) * 8)
+    k.b200_pcg_solve(pcg, bvec.ptr, 2, 0.0, 0.0, KCG, 0.15, 10)
 k.b200_sync()
 print("done", k.b200_last_error())
