@@ -42,11 +42,11 @@ $(LIBDIR)/libb200_kernels_f32.so: $(CU_SRC) $(CU_HDR)
 
 $(LIBDIR)/libosqp_b200_f64.so: $(LIBDIR)/libb200_kernels_f64.so $(ALG_SRC) $(ALG_HDR)
 	$(CC) $(CFLAGS) $(CINC) -shared -Wl,-Bsymbolic -o $@ $(CORE_SRC) $(ALG_SRC) \
-	    -L$(LIBDIR) -lb200_kernels_f64 -Wl,-rpath,'$$ORIGIN' -lm
+	    -L$(LIBDIR) -lb200_kernels_f64 -Wl,-rpath,'$$ORIGIN' -lm -lpthread
 
 $(LIBDIR)/libosqp_b200_f32.so: $(LIBDIR)/libb200_kernels_f32.so $(ALG_SRC) $(ALG_HDR)
 	$(CC) $(CFLAGS) -DB200_USE_FLOAT $(CINC) -shared -Wl,-Bsymbolic -o $@ $(CORE_SRC) $(ALG_SRC) \
-	    -L$(LIBDIR) -lb200_kernels_f32 -Wl,-rpath,'$$ORIGIN' -lm
+	    -L$(LIBDIR) -lb200_kernels_f32 -Wl,-rpath,'$$ORIGIN' -lm -lpthread
 
 oracle:
 	$(MAKE) -C oracle REF=$(REF)

@@ -11,6 +11,15 @@
  */
 #include "pcg_interface.h"
 #include "glob_opts.h"
+#include <stdio.h>
+#include <stdlib.h>
+#include <time.h>
+
+static double now_ms(void) {
+  struct timespec ts;
+  clock_gettime(CLOCK_MONOTONIC, &ts);
+  return 1e3 * ts.tv_sec + 1e-6 * ts.tv_nsec;
+}
 
 static const char* name_b200pcg(b200pcg_solver* s) {
   switch (s->precond_type) {
@@ -117,12 +126,14 @@ OSQPInt init_linsys_solver_b200pcg(b200pcg_solver** sp, const OSQPMatrix* P, con
   s->update_rho_vec     = &update_rho_vec_b200pcg;
   s->update_settings    = &update_settings_b200pcg;
 
+  double t0 = now_ms();
   s->pcg = b200_pcg_create(P->S, A->S, A->St, (int)s->n, (int)s->m);
   if (!s->pcg) return OSQP_MEM_ALLOC_ERROR;
 
   configure(s);
   b200_pcg_refresh_matrices(s->pcg);
   b200_pcg_refresh_precond(s->pcg);
+  if (getenv("B200_TRACE_SETUP")) { b200_sync(); fprintf(stderr, "[b200 trace] linsys init %.1f ms\n", now_ms() - t0); }
   return 0;
 }
 
