@@ -40,12 +40,27 @@ $(LIBDIR)/libb200_kernels_f32.so: $(CU_SRC) $(CU_HDR)
 	@mkdir -p $(LIBDIR)
 	$(NVCC) $(NVFLAGS) -DB200_USE_FLOAT -shared -o $@ $(CU_SRC) -cudart static
 
-$(LIBDIR)/libosqp_b200_f64.so: $(LIBDIR)/libb200_kernels_f64.so $(ALG_SRC) $(ALG_HDR)
-	$(CC) $(CFLAGS) $(CINC) -shared -Wl,-Bsymbolic -o $@ $(CORE_SRC) $(ALG_SRC) \
+# auxil.c is compiled from the reference tree UNCHANGED, with four of its functions renamed on the
+# command line so that algebra/b200/fused_admm.c can provide the fused versions (see that file)
+FUSE_RENAMES := -Dupdate_xz_tilde=osqp_ref_update_xz_tilde -Dupdate_x=osqp_ref_update_x \
+                -Dupdate_z=osqp_ref_update_z -Dupdate_y=osqp_ref_update_y \
+                -Dupdate_info=osqp_ref_update_info
+CORE_REST    := $(filter-out $(REF)/src/auxil.c,$(CORE_SRC))
+
+$(LIBDIR)/auxil_f64.o: $(REF)/src/auxil.c Makefile
+	@mkdir -p $(LIBDIR)
+	$(CC) $(CFLAGS) $(CINC) $(FUSE_RENAMES) -c -o $@ $<
+
+$(LIBDIR)/auxil_f32.o: $(REF)/src/auxil.c Makefile
+	@mkdir -p $(LIBDIR)
+	$(CC) $(CFLAGS) -DB200_USE_FLOAT $(CINC) $(FUSE_RENAMES) -c -o $@ $<
+
+$(LIBDIR)/libosqp_b200_f64.so: $(LIBDIR)/libb200_kernels_f64.so $(LIBDIR)/auxil_f64.o $(ALG_SRC) $(ALG_HDR)
+	$(CC) $(CFLAGS) $(CINC) -shared -Wl,-Bsymbolic -o $@ $(CORE_REST) $(LIBDIR)/auxil_f64.o $(ALG_SRC) \
 	    -L$(LIBDIR) -lb200_kernels_f64 -Wl,-rpath,'$$ORIGIN' -lm -lpthread
 
-$(LIBDIR)/libosqp_b200_f32.so: $(LIBDIR)/libb200_kernels_f32.so $(ALG_SRC) $(ALG_HDR)
-	$(CC) $(CFLAGS) -DB200_USE_FLOAT $(CINC) -shared -Wl,-Bsymbolic -o $@ $(CORE_SRC) $(ALG_SRC) \
+$(LIBDIR)/libosqp_b200_f32.so: $(LIBDIR)/libb200_kernels_f32.so $(LIBDIR)/auxil_f32.o $(ALG_SRC) $(ALG_HDR)
+	$(CC) $(CFLAGS) -DB200_USE_FLOAT $(CINC) -shared -Wl,-Bsymbolic -o $@ $(CORE_REST) $(LIBDIR)/auxil_f32.o $(ALG_SRC) \
 	    -L$(LIBDIR) -lb200_kernels_f32 -Wl,-rpath,'$$ORIGIN' -lm -lpthread
 
 oracle:

@@ -44,6 +44,27 @@ struct OSQPMatrix_ {
   OSQPInt*  h_map2;   /* P only: position of the mirrored copy, -1 on diagonal   */
 };
 
+/*
+ * Scalar cache: the fused termination check (fused_admm.c) computes every norm the core asks for
+ * right afterwards (compute_prim_tol / compute_dual_tol / compute_rho_estimate, src/auxil.c:14-47,
+ * 334-458) in one kernel and parks them here keyed by (weight pointer, vector pointer).  An entry is
+ * served only while b200_epoch() is unchanged, i.e. as long as no kernel or copy that could have
+ * modified a vector has been issued since -- otherwise the reduction is recomputed as usual.
+ */
+#define B200_NORM_CACHE_MAX 12
+typedef struct {
+  unsigned long long epoch;
+  int                count;
+  const void*        s[B200_NORM_CACHE_MAX];   /* weight vector data pointer or NULL */
+  const void*        v[B200_NORM_CACHE_MAX];
+  OSQPFloat          val[B200_NORM_CACHE_MAX];
+} b200_norm_cache;
+
+void b200_norm_cache_reset(void);
+void b200_norm_cache_put(const void* s, const void* v, OSQPFloat val);
+void b200_norm_cache_seal(void);                       /* stamp with the current epoch */
+int  b200_norm_cache_get(const void* s, const void* v, OSQPFloat* val);
+
 #ifdef __cplusplus
 }
 #endif

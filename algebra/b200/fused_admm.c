@@ -1,0 +1,167 @@
+/*
+ * algebra/b200/fused_admm.c -- fused ADMM steps for the product build.
+ *
+ * The private algebra interface is per-op, so the unmodified core spends 5 kernels on
+ * compute_rhs (src/auxil.c:136-158) and 16 on update_x / update_z / update_y (auxil.c:172-229)
+ * where two suffice.  auxil.c stays BYTE-IDENTICAL: the Makefile compiles it with
+ *     -Dupdate_xz_tilde=osqp_ref_update_xz_tilde -Dupdate_x=osqp_ref_update_x
+ *     -Dupdate_z=osqp_ref_update_z -Dupdate_y=osqp_ref_update_y
+ * so that the reference definitions keep existing under the osqp_ref_ names (and can be selected
+ * at run time with OSQP_B200_UNFUSED=1 for A/B parity runs), while the calls made by
+ * src/osqp_api.c:708-726 bind to the versions below.  Expression order follows the reference's
+ * add_scaled / add_scaled3 / ew_prod calls term by term.
+ */
+#include "osqp.h"
+#include "auxil.h"
+#include "types.h"
+#include "algebra_impl.h"
+#include "timing.h"
+#include "glob_opts.h"
+
+#include <stdlib.h>
+
+void osqp_ref_update_xz_tilde(OSQPSolver* solver, OSQPInt admm_iter);
+void osqp_ref_update_x(OSQPSolver* solver);
+void osqp_ref_update_z(OSQPSolver* solver);
+void osqp_ref_update_y(OSQPSolver* solver);
+void osqp_ref_update_info(OSQPSolver* solver, OSQPInt iter, OSQPInt polishing);
+
+static int unfused(void) {
+  static int v = -1;
+  if (v < 0) v = getenv("OSQP_B200_UNFUSED") ? 1 : 0;
+  return v;
+}
+
+/* compute_rhs + LinSysSolver.solve (auxil.c:136-170) */
+void update_xz_tilde(OSQPSolver* solver, OSQPInt admm_iter) {
+  OSQPWorkspace* work     = solver->work;
+  OSQPSettings*  settings = solver->settings;
+
+  if (unfused()) {
+    osqp_ref_update_xz_tilde(solver, admm_iter);
+    return;
+  }
+  b200_admm_compute_rhs(work->xtilde_view->d_val, work->ztilde_view->d_val, work->x_prev->d_val,
+                        work->data->q->d_val, work->z_prev->d_val, work->y->d_val,
+                        settings->rho_is_vec ? work->rho_inv_vec->d_val : OSQP_NULL, work->rho_inv,
+                        settings->sigma, (int)work->data->n, (int)work->data->m);
+  work->linsys_solver->solve(work->linsys_solver, work->xz_tilde, admm_iter);
+}
+
+/* update_x, update_z and update_y (auxil.c:172-229) in one kernel; osqp_solve calls the three
+ * back to back (osqp_api.c:714-722), so the z and y halves are done here and the other two
+ * entry points have nothing left to do. */
+void update_x(OSQPSolver* solver) {
+  OSQPWorkspace* work     = solver->work;
+  OSQPSettings*  settings = solver->settings;
+  int            vec      = settings->rho_is_vec ? 1 : 0;
+
+  if (unfused()) {
+    osqp_ref_update_x(solver);
+    return;
+  }
+  b200_admm_update_xzy(work->x->d_val, work->delta_x->d_val, work->z->d_val, work->y->d_val,
+                       work->delta_y->d_val, work->xtilde_view->d_val, work->ztilde_view->d_val,
+                       work->x_prev->d_val, work->z_prev->d_val, work->data->l->d_val,
+                       work->data->u->d_val, vec ? work->rho_vec->d_val : OSQP_NULL,
+                       vec ? work->rho_inv_vec->d_val : OSQP_NULL, settings->rho, work->rho_inv,
+                       settings->alpha, (int)work->data->n, (int)work->data->m);
+}
+
+void update_z(OSQPSolver* solver) {
+  if (unfused()) osqp_ref_update_z(solver);
+}
+
+void update_y(OSQPSolver* solver) {
+  if (unfused()) osqp_ref_update_y(solver);
+}
+
+/* update_info for the ADMM iterates (auxil.c:676-762 with compute_prim_res :308, compute_dual_res
+ * :371 and compute_obj_val_dual_gap :231 inlined).  Side effects kept: work->Ax / Px / Aty are
+ * materialised (read by later core code); the scratch uses of x_prev / z_prev are dropped (dead
+ * until the swap at the top of the next iteration). */
+void update_info(OSQPSolver* solver, OSQPInt iter, OSQPInt polishing) {
+  OSQPInfo*      info     = solver->info;
+  OSQPSettings*  settings = solver->settings;
+  OSQPWorkspace* work     = solver->work;
+  OSQPInt        n = work->data->n, m = work->data->m;
+  int            unscale  = settings->scaling && !settings->scaled_termination;
+  double         r[B200_RES_COUNT];
+  OSQPFloat      quad_term, lin_term, sup_term, prim_res, dual_res;
+
+  if (polishing || unfused()) {
+    osqp_ref_update_info(solver, iter, polishing);
+    return;
+  }
+  info->iter = iter;
+
+  if (m) OSQPMatrix_Axpy(work->data->A, work->x, work->Ax, 1.0, 0.0);
+  OSQPMatrix_Axpy(work->data->P, work->x, work->Px, 1.0, 0.0);
+  if (m) OSQPMatrix_Atxpy(work->data->A, work->y, work->Aty, 1.0, 0.0);
+
+  b200_admm_residuals(work->x->d_val, work->y->d_val, work->z->d_val, work->Ax->d_val,
+                      work->Px->d_val, work->Aty->d_val, work->data->q->d_val, work->data->l->d_val,
+                      work->data->u->d_val, settings->scaling ? work->scaling->Einv->d_val : OSQP_NULL,
+                      settings->scaling ? work->scaling->Dinv->d_val : OSQP_NULL,
+                      OSQP_INFTY * OSQP_MIN_SCALING, OSQP_ZERO_DEADZONE, (int)n, (int)m, r);
+
+  /* primal residual (compute_prim_res) */
+  if (m == 0) {
+    prim_res = 0.;
+  } else {
+    work->scaled_prim_res = (OSQPFloat)r[B200_RES_PRIM_S];
+    prim_res = unscale ? (OSQPFloat)r[B200_RES_PRIM_U] : work->scaled_prim_res;
+  }
+  /* dual residual (compute_dual_res) */
+  work->scaled_dual_res = (OSQPFloat)r[B200_RES_DUAL_S];
+  dual_res = unscale ? work->scaling->cinv * (OSQPFloat)r[B200_RES_DUAL_U] : work->scaled_dual_res;
+  info->prim_res = prim_res;
+  info->dual_res = dual_res;
+
+  /* objective and duality gap (compute_obj_val_dual_gap) */
+  quad_term = (OSQPFloat)r[B200_RES_XPX];
+  lin_term  = (OSQPFloat)r[B200_RES_QX];
+  sup_term  = (OSQPFloat)r[B200_RES_SC];
+  info->obj_val         = 0.5 * quad_term + lin_term;
+  info->dual_obj_val    = -0.5 * quad_term - sup_term;
+  work->scaled_dual_gap = quad_term + lin_term + sup_term;
+  if (settings->scaling) {
+    info->obj_val      *= work->scaling->cinv;
+    info->dual_obj_val *= work->scaling->cinv;
+    info->duality_gap   = work->scaling->cinv * work->scaled_dual_gap;
+  } else {
+    info->duality_gap = work->scaled_dual_gap;
+  }
+  work->xtPx = quad_term;
+  work->qtx  = lin_term;
+  work->SC   = sup_term;
+
+  info->primdual_int += c_absval(info->duality_gap);
+#ifdef OSQP_ENABLE_PROFILING
+  info->solve_time = osqp_toc(work->timer);
+#endif
+  info->rel_kkt_error = c_max(c_max(info->dual_res, info->prim_res), info->duality_gap);
+#ifdef OSQP_ENABLE_PRINTING
+  work->summary_printed = 0;
+#endif
+
+  /* norms the core asks for next, valid until the next kernel or copy */
+  b200_norm_cache_reset();
+  if (m) {
+    b200_norm_cache_put(OSQP_NULL, work->z->d_val, (OSQPFloat)r[B200_RES_Z_S]);
+    b200_norm_cache_put(OSQP_NULL, work->Ax->d_val, (OSQPFloat)r[B200_RES_AX_S]);
+    b200_norm_cache_put(OSQP_NULL, work->Aty->d_val, (OSQPFloat)r[B200_RES_ATY_S]);
+  }
+  b200_norm_cache_put(OSQP_NULL, work->data->q->d_val, (OSQPFloat)r[B200_RES_Q_S]);
+  b200_norm_cache_put(OSQP_NULL, work->Px->d_val, (OSQPFloat)r[B200_RES_PX_S]);
+  if (settings->scaling) {
+    if (m) {
+      b200_norm_cache_put(work->scaling->Einv->d_val, work->z->d_val, (OSQPFloat)r[B200_RES_Z_U]);
+      b200_norm_cache_put(work->scaling->Einv->d_val, work->Ax->d_val, (OSQPFloat)r[B200_RES_AX_U]);
+      b200_norm_cache_put(work->scaling->Dinv->d_val, work->Aty->d_val, (OSQPFloat)r[B200_RES_ATY_U]);
+    }
+    b200_norm_cache_put(work->scaling->Dinv->d_val, work->data->q->d_val, (OSQPFloat)r[B200_RES_Q_U]);
+    b200_norm_cache_put(work->scaling->Dinv->d_val, work->Px->d_val, (OSQPFloat)r[B200_RES_PX_U]);
+  }
+  b200_norm_cache_seal();
+}

@@ -232,11 +232,42 @@ void OSQPVectorf_set_scalar_if_gt(OSQPVectorf* x, const OSQPVectorf* z, OSQPFloa
 /* ------------------------------------------------------------------ reductions
  * each returns a host scalar by value and is therefore one stream synchronisation */
 
+static b200_norm_cache g_cache;
+
+void b200_norm_cache_reset(void) { g_cache.count = 0; g_cache.epoch = 0; }
+
+void b200_norm_cache_put(const void* s, const void* v, OSQPFloat val) {
+  if (g_cache.count < B200_NORM_CACHE_MAX) {
+    g_cache.s[g_cache.count]   = s;
+    g_cache.v[g_cache.count]   = v;
+    g_cache.val[g_cache.count] = val;
+    g_cache.count++;
+  }
+}
+
+void b200_norm_cache_seal(void) { g_cache.epoch = b200_epoch(); }
+
+int b200_norm_cache_get(const void* s, const void* v, OSQPFloat* val) {
+  int i;
+  if (g_cache.count == 0 || g_cache.epoch != b200_epoch()) return 0;
+  for (i = 0; i < g_cache.count; i++) {
+    if (g_cache.s[i] == s && g_cache.v[i] == v) {
+      *val = g_cache.val[i];
+      return 1;
+    }
+  }
+  return 0;
+}
+
 OSQPFloat OSQPVectorf_norm_inf(const OSQPVectorf* v) {
+  OSQPFloat cached;
+  if (b200_norm_cache_get(OSQP_NULL, v->d_val, &cached)) return cached;
   return b200_vec_norm_inf(v->d_val, v->length);
 }
 
 OSQPFloat OSQPVectorf_scaled_norm_inf(const OSQPVectorf* S, const OSQPVectorf* v) {
+  OSQPFloat cached;
+  if (b200_norm_cache_get(S->d_val, v->d_val, &cached)) return cached;
   return b200_vec_scaled_norm_inf(S->d_val, v->d_val, v->length);
 }
 

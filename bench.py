@@ -276,11 +276,12 @@ def run_b200(args):
         e2e_step()
     barrier()
     t0 = time.perf_counter()
-    e_iters, setup_s = 0, 0.0
+    e_iters, setup_s, e_steps = 0, 0.0, []
     for _ in range(args.steps):
         it, dt, st = e2e_step()
         e_iters += it
         setup_s += st
+        e_steps.append(round(1e3 * dt, 1))
     barrier()
     e_total = time.perf_counter() - t0
     fi = F if prec == "f64" else 4
@@ -305,9 +306,12 @@ def run_b200(args):
         roof = pcg_roofline(k, pb, kcg) if prec == "f64" else None
         traffic = None
         tp = ROOT / "profiles" / "pcg_traffic.json"
-        if tp.exists():
+        if tp.exists() and roof is not None:
             try:
-                traffic = json.loads(tp.read_text()).get("dram_bytes_per_launch")
+                tj = json.loads(tp.read_text())
+                # only comparable when the ncu capture ran the same number of CG iterations per launch
+                if tj.get("cg_iters_per_launch") == roof["cg_iters_per_launch"]:
+                    traffic = tj.get("dram_bytes_per_launch")
             except (ValueError, OSError):
                 traffic = None
         cpu = None
@@ -344,7 +348,7 @@ def run_b200(args):
             "status": status, "obj_val": obj,
             "e2e": {"value": e_iters / e_total, "unit": "iter/s", "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h, "time_to_solution_ms": 1e3 * e_total / args.steps,
-                    "setup_ms": 1e3 * setup_s / args.steps,
+                    "setup_ms": 1e3 * setup_s / args.steps, "step_ms": e_steps,
                     "step": "osqp_setup from host CSC arrays + osqp_solve + solution to host"},
             "gpu_launches": int(launches),
             "clocks": clocks,

@@ -202,6 +202,26 @@ void b200_admm_update_xzy(b200_float* d_x, b200_float* d_delta_x, b200_float* d_
                           const b200_float* d_rho_vec, const b200_float* d_rho_inv_vec,
                           b200_float rho, b200_float rho_inv, b200_float alpha, int n, int m);
 
+/* All reductions of one termination check in ONE kernel + ONE device->host copy, instead of the
+ * ~13 synchronising reductions and ~7 elementwise kernels of update_info / compute_prim_res /
+ * compute_dual_res / compute_obj_val_dual_gap / compute_*_tol / compute_rho_estimate
+ * (src/auxil.c:14-47,231-458,676-762).  Inputs: x, y, z and the products Ax, Px, Aty (already
+ * computed), q, l, u and the scaling vectors (NULL when scaling is off).  h_out[17] receives, in
+ * the order of B200_RES_*: maxima are inf-norms, *_U are the Einv/Dinv-weighted ones. */
+enum {
+  B200_RES_PRIM_S = 0, B200_RES_PRIM_U, B200_RES_Z_S, B200_RES_Z_U, B200_RES_AX_S, B200_RES_AX_U,
+  B200_RES_SC, B200_RES_DUAL_S, B200_RES_DUAL_U, B200_RES_Q_S, B200_RES_Q_U, B200_RES_PX_S,
+  B200_RES_PX_U, B200_RES_ATY_S, B200_RES_ATY_U, B200_RES_XPX, B200_RES_QX, B200_RES_COUNT
+};
+void b200_admm_residuals(const b200_float* d_x, const b200_float* d_y, const b200_float* d_z,
+                         const b200_float* d_Ax, const b200_float* d_Px, const b200_float* d_Aty,
+                         const b200_float* d_q, const b200_float* d_l, const b200_float* d_u,
+                         const b200_float* d_Einv, const b200_float* d_Dinv, b200_float infval,
+                         b200_float deadzone, int n, int m, double* h_out);
+/* bumped by every kernel launch / device copy of the library: lets the backend cache scalars and
+ * know when they went stale */
+unsigned long long b200_epoch(void);
+
 #ifdef __cplusplus
 }
 #endif

@@ -14,7 +14,7 @@ namespace b200 {
 
 constexpr int kBlock        = 256;    // threads per CTA for every kernel in the library
 constexpr int kMaxRedBlocks = 1184;   // 148 SMs x 8 CTAs: upper bound for reduction grids
-constexpr int kScalarSlots  = 16;
+constexpr int kScalarSlots  = 32;
 
 struct Context {
   int          refcount   = 0;
@@ -30,6 +30,7 @@ struct Context {
   // staging buffer for host->device index/value uploads is allocated on demand
   int          last_error = 0;
   unsigned long long launches = 0;
+  unsigned long long epoch    = 0;   // launches + device copies: anything that may change a vector
   char         name[256]  = {0};
 };
 
@@ -47,9 +48,23 @@ inline bool check(cudaError_t e, const char* what) {
 
 #define B200_CHECK(expr) ::b200::check((expr), #expr)
 
+// Stream-ordered allocation from the device's default memory pool (release threshold raised to
+// "never" in b200_init): setting a solver up and tearing it down again recycles the same physical
+// memory instead of going through cudaMalloc/cudaFree (each a device synchronisation and, for
+// the 100 MB+ matrix arrays, milliseconds of page mapping -- measured as 100-1000 ms outliers in
+// the end-to-end setup time).
+template <class P>
+inline cudaError_t dev_malloc(P** p, size_t bytes) {
+  return cudaMallocAsync((void**)p, bytes ? bytes : 8, ctx().stream);
+}
+inline void dev_free(void* p) {
+  if (p) cudaFreeAsync(p, ctx().stream);
+}
+
 // called after every kernel launch: counts it and records (sticky) launch-configuration errors
 inline void count_launch() {
   ctx().launches++;
+  ctx().epoch++;
   cudaError_t e = cudaPeekAtLastError();
   if (e != cudaSuccess) check(cudaGetLastError(), "kernel launch");
 }

@@ -41,10 +41,17 @@ int b200_init(int device) {
   snprintf(c.name, sizeof(c.name), "%s (sm_%d%d, %d SMs)", prop.name, prop.major, prop.minor,
            prop.multiProcessorCount);
   if (!B200_CHECK(cudaStreamCreateWithFlags(&c.stream, cudaStreamNonBlocking))) return 1;
+  {
+    cudaMemPool_t pool;
+    if (B200_CHECK(cudaDeviceGetDefaultMemPool(&pool, device))) {
+      unsigned long long keep = ~0ull;   // never hand memory back to the driver between solvers
+      B200_CHECK(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
+    }
+  }
   bool ok = true;
-  ok &= B200_CHECK(cudaMalloc(&c.d_partials, sizeof(double) * kMaxRedBlocks * 4));
-  ok &= B200_CHECK(cudaMalloc(&c.d_ticket, sizeof(unsigned) * 4));
-  ok &= B200_CHECK(cudaMalloc(&c.d_scalar, sizeof(double) * kScalarSlots));
+  ok &= B200_CHECK(dev_malloc(&c.d_partials, sizeof(double) * kMaxRedBlocks * 32));
+  ok &= B200_CHECK(dev_malloc(&c.d_ticket, sizeof(unsigned) * 4));
+  ok &= B200_CHECK(dev_malloc(&c.d_scalar, sizeof(double) * kScalarSlots));
   ok &= B200_CHECK(cudaMallocHost(&c.h_scalar, sizeof(double) * kScalarSlots));
   if (!ok) return 1;
   B200_CHECK(cudaMemsetAsync(c.d_ticket, 0, sizeof(unsigned) * 4, c.stream));
@@ -62,9 +69,9 @@ void b200_shutdown(void) {
   if (c.refcount <= 0) return;
   if (--c.refcount > 0) return;
   cudaStreamSynchronize(c.stream);
-  cudaFree(c.d_partials);
-  cudaFree(c.d_ticket);
-  cudaFree(c.d_scalar);
+  dev_free(c.d_partials);
+  dev_free(c.d_ticket);
+  dev_free(c.d_scalar);
   cudaFreeHost(c.h_scalar);
   cudaStreamDestroy(c.stream);
   c.d_partials = nullptr;
@@ -91,6 +98,8 @@ int b200_last_error(void) { return ctx().last_error; }
 
 unsigned long long b200_launch_count(void) { return ctx().launches; }
 
+unsigned long long b200_epoch(void) { return ctx().epoch; }
+
 void* b200_event_create(void) {
   cudaEvent_t e = nullptr;
   if (!B200_CHECK(cudaEventCreate(&e))) return nullptr;
@@ -109,8 +118,9 @@ float b200_event_elapsed_ms(void* a, void* b) {
 
 void* b200_malloc(size_t bytes) {
   void* p = nullptr;
+  ctx().epoch++;   // addresses may be reused: cached scalars keyed by pointer go stale
   if (bytes == 0) bytes = 8;   // keep zero-length vectors addressable
-  if (!B200_CHECK(cudaMalloc(&p, bytes))) return nullptr;
+  if (!B200_CHECK(dev_malloc(&p, bytes))) return nullptr;
   return p;
 }
 
@@ -122,8 +132,9 @@ void* b200_calloc(size_t bytes) {
 
 void b200_free(void* d_ptr) {
   if (!d_ptr) return;
-  // cudaFree synchronises the device, so in-flight kernels using d_ptr finish first
-  B200_CHECK(cudaFree(d_ptr));
+  ctx().epoch++;
+  // stream-ordered: kernels already enqueued on the library stream finish before reuse
+  dev_free(d_ptr);
 }
 
 int b200_ptr_is_device(const void* ptr) {
@@ -138,6 +149,7 @@ int b200_ptr_is_device(const void* ptr) {
 int b200_copy_in(void* d_dst, const void* src, size_t bytes) {
   if (bytes == 0) return 0;
   Context& c = ctx();
+  c.epoch++;
   if (b200_ptr_is_device(src)) {
     return B200_CHECK(cudaMemcpyAsync(d_dst, src, bytes, cudaMemcpyDeviceToDevice, c.stream)) ? 0 : 1;
   }

@@ -52,10 +52,10 @@ int b200_build_schedule(b200_csr* M, const int* rp) {
   M->nlong   = (int)longs.size();
   Context& c = ctx();
   bool ok = true;
-  ok &= B200_CHECK(cudaMalloc(&M->d_desc, sizeof(int4) * (desc.size() + 1)));
-  ok &= B200_CHECK(cudaMalloc(&M->d_long, sizeof(int4) * (longs.size() + 1)));
-  ok &= B200_CHECK(cudaMalloc(&M->d_long_partials, sizeof(double) * (desc.size() + 1)));
-  ok &= B200_CHECK(cudaMalloc(&M->d_long_counters, sizeof(unsigned) * (longs.size() + 1)));
+  ok &= B200_CHECK(dev_malloc(&M->d_desc, sizeof(int4) * (desc.size() + 1)));
+  ok &= B200_CHECK(dev_malloc(&M->d_long, sizeof(int4) * (longs.size() + 1)));
+  ok &= B200_CHECK(dev_malloc(&M->d_long_partials, sizeof(double) * (desc.size() + 1)));
+  ok &= B200_CHECK(dev_malloc(&M->d_long_counters, sizeof(unsigned) * (longs.size() + 1)));
   if (!ok) return 1;
   if (!desc.empty())
     ok &= B200_CHECK(cudaMemcpyAsync(M->d_desc, desc.data(), sizeof(int4) * desc.size(),
@@ -196,10 +196,10 @@ b200_csr* b200_csr_create(int nrows, int ncols, int nnz, const int* h_row_ptr, c
   b200_csr* M = new b200_csr();
   M->nrows = nrows; M->ncols = ncols; M->nnz = nnz;
   bool ok = true;
-  ok &= B200_CHECK(cudaMalloc(&M->d_row_ptr, sizeof(int) * ((size_t)nrows + 2 * kPad)));
+  ok &= B200_CHECK(dev_malloc(&M->d_row_ptr, sizeof(int) * ((size_t)nrows + 2 * kPad)));
   // kPad slack: the TMA copies start 16-byte aligned-down and end 16-byte rounded-up
-  ok &= B200_CHECK(cudaMalloc(&M->d_col_ind, sizeof(int) * ((size_t)nnz + 2 * kPad)));
-  ok &= B200_CHECK(cudaMalloc(&M->d_val, sizeof(T) * ((size_t)nnz + 2 * kPad)));
+  ok &= B200_CHECK(dev_malloc(&M->d_col_ind, sizeof(int) * ((size_t)nnz + 2 * kPad)));
+  ok &= B200_CHECK(dev_malloc(&M->d_val, sizeof(T) * ((size_t)nnz + 2 * kPad)));
   if (!ok) { b200_csr_destroy(M); return nullptr; }
   ok &= B200_CHECK(cudaMemcpyAsync(M->d_row_ptr, h_row_ptr, sizeof(int) * ((size_t)nrows + 1),
                                    cudaMemcpyHostToDevice, c.stream));
@@ -215,13 +215,13 @@ b200_csr* b200_csr_create(int nrows, int ncols, int nnz, const int* h_row_ptr, c
 
 void b200_csr_destroy(b200_csr* M) {
   if (!M) return;
-  cudaFree(M->d_row_ptr);
-  cudaFree(M->d_col_ind);
-  cudaFree(M->d_val);
-  cudaFree(M->d_desc);
-  cudaFree(M->d_long);
-  cudaFree(M->d_long_partials);
-  cudaFree(M->d_long_counters);
+  dev_free(M->d_row_ptr);
+  dev_free(M->d_col_ind);
+  dev_free(M->d_val);
+  dev_free(M->d_desc);
+  dev_free(M->d_long);
+  dev_free(M->d_long_partials);
+  dev_free(M->d_long_counters);
   delete M;
 }
 

@@ -280,11 +280,11 @@ b200_pcg* b200_pcg_create(const b200_csr* P, const b200_csr* A, const b200_csr* 
   b200_pcg* s = new b200_pcg();
   s->P = P; s->A = A; s->At = At; s->n = n; s->m = m;
   bool ok = true;
-  auto alloc = [&](T** p, size_t cnt) { ok &= B200_CHECK(cudaMalloc(p, sizeof(T) * (cnt + 1))); };
+  auto alloc = [&](T** p, size_t cnt) { ok &= B200_CHECK(dev_malloc(p, sizeof(T) * (cnt + 1))); };
   alloc(&s->d_x, n); alloc(&s->d_p, n); alloc(&s->d_Kp, n); alloc(&s->d_r, n);
   alloc(&s->d_t, m); alloc(&s->d_minv, n); alloc(&s->d_pd, n); alloc(&s->d_ad, n);
   alloc(&s->d_Ax, m); alloc(&s->d_w, m);
-  ok &= B200_CHECK(cudaMalloc(&s->d_state, sizeof(PcgState)));
+  ok &= B200_CHECK(dev_malloc(&s->d_state, sizeof(PcgState)));
   if (!ok) { b200_pcg_destroy(s); return nullptr; }
   B200_CHECK(cudaMemsetAsync(s->d_x, 0, sizeof(T) * (n + 1), c.stream));   // PCG iterate starts at 0
   B200_CHECK(cudaMemsetAsync(s->d_state, 0, sizeof(PcgState), c.stream));
@@ -299,9 +299,9 @@ b200_pcg* b200_pcg_create(const b200_csr* P, const b200_csr* A, const b200_csr* 
   for (int i = 0; i <= n; i++) rp[i] = rpP[i] + rpAt[i];
   b200_csr& K = s->K2;
   K.nrows = n; K.ncols = n + m; K.nnz = rp[n];
-  ok &= B200_CHECK(cudaMalloc(&K.d_row_ptr, sizeof(int) * ((size_t)n + 2 * kPad)));
-  ok &= B200_CHECK(cudaMalloc(&K.d_col_ind, sizeof(int) * ((size_t)K.nnz + 2 * kPad)));
-  ok &= B200_CHECK(cudaMalloc(&K.d_val, sizeof(T) * ((size_t)K.nnz + 2 * kPad)));
+  ok &= B200_CHECK(dev_malloc(&K.d_row_ptr, sizeof(int) * ((size_t)n + 2 * kPad)));
+  ok &= B200_CHECK(dev_malloc(&K.d_col_ind, sizeof(int) * ((size_t)K.nnz + 2 * kPad)));
+  ok &= B200_CHECK(dev_malloc(&K.d_val, sizeof(T) * ((size_t)K.nnz + 2 * kPad)));
   if (!ok) { b200_pcg_destroy(s); return nullptr; }
   ok &= B200_CHECK(cudaMemcpyAsync(K.d_row_ptr, rp.data(), sizeof(int) * (n + 1), cudaMemcpyHostToDevice, c.stream));
   ok &= B200_CHECK(cudaStreamSynchronize(c.stream));
@@ -319,7 +319,7 @@ b200_pcg* b200_pcg_create(const b200_csr* P, const b200_csr* A, const b200_csr* 
   if (ew > want) want = ew;
   if (want < 1) want = 1;
   s->grid = (int)(want < s->max_grid ? want : s->max_grid);
-  ok &= B200_CHECK(cudaMalloc(&s->d_red, sizeof(double) * SLOT_COUNT * s->max_grid));
+  ok &= B200_CHECK(dev_malloc(&s->d_red, sizeof(double) * SLOT_COUNT * s->max_grid));
   if (!ok) { b200_pcg_destroy(s); return nullptr; }
   // driver choice: the graph driver (lean kernels, WHILE node) pays ~8 launches per solve
   // (measured round 1: the two drivers are within 5 % of each other on the 1.14e7-nnz Lasso, so the
@@ -337,14 +337,14 @@ b200_pcg* b200_pcg_create(const b200_csr* P, const b200_csr* A, const b200_csr* 
 
 void b200_pcg_destroy(b200_pcg* s) {
   if (!s) return;
-  cudaFree(s->d_x); cudaFree(s->d_p); cudaFree(s->d_Kp); cudaFree(s->d_r); cudaFree(s->d_t);
-  cudaFree(s->d_Ax); cudaFree(s->d_w);
-  cudaFree(s->d_minv); cudaFree(s->d_pd); cudaFree(s->d_ad);
+  dev_free(s->d_x); dev_free(s->d_p); dev_free(s->d_Kp); dev_free(s->d_r); dev_free(s->d_t);
+  dev_free(s->d_Ax); dev_free(s->d_w);
+  dev_free(s->d_minv); dev_free(s->d_pd); dev_free(s->d_ad);
   b200_pcg_graph_destroy(s);
-  cudaFree(s->d_state); cudaFree(s->d_red);
-  cudaFree(s->K2.d_row_ptr); cudaFree(s->K2.d_col_ind); cudaFree(s->K2.d_val);
-  cudaFree(s->K2.d_desc); cudaFree(s->K2.d_long); cudaFree(s->K2.d_long_partials);
-  cudaFree(s->K2.d_long_counters);
+  dev_free(s->d_state); dev_free(s->d_red);
+  dev_free(s->K2.d_row_ptr); dev_free(s->K2.d_col_ind); dev_free(s->K2.d_val);
+  dev_free(s->K2.d_desc); dev_free(s->K2.d_long); dev_free(s->K2.d_long_partials);
+  dev_free(s->K2.d_long_counters);
   delete s;
 }
 
@@ -380,6 +380,7 @@ void b200_pcg_refresh_precond(b200_pcg* s) {
 }
 
 void b200_pcg_warm_start(b200_pcg* s, const T* d_x) {
+  ctx().epoch++;
   s->ax_valid = 0;   // the iterate is replaced: the carried A x is stale
   if (s->n > 0)
     B200_CHECK(cudaMemcpyAsync(s->d_x, d_x, sizeof(T) * s->n, cudaMemcpyDeviceToDevice, ctx().stream));

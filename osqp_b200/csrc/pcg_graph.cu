@@ -302,9 +302,9 @@ int b200_pcg_graph_build(b200_pcg* s) {
   Context& c = ctx();
   bool ok = true;
   s->gred_stride = c.sm_count * 32;
-  ok &= B200_CHECK(cudaMalloc(&s->d_args, sizeof(PcgArgs)));
-  ok &= B200_CHECK(cudaMalloc(&s->d_run, sizeof(PcgRun)));
-  ok &= B200_CHECK(cudaMalloc(&s->d_gred, sizeof(double) * SLOT_COUNT * s->gred_stride));
+  ok &= B200_CHECK(dev_malloc(&s->d_args, sizeof(PcgArgs)));
+  ok &= B200_CHECK(dev_malloc(&s->d_run, sizeof(PcgRun)));
+  ok &= B200_CHECK(dev_malloc(&s->d_gred, sizeof(double) * SLOT_COUNT * s->gred_stride));
   if (!ok) return 1;
   B200_CHECK(cudaMemsetAsync(s->d_run, 0, sizeof(PcgRun), c.stream));
 
@@ -377,9 +377,9 @@ int b200_pcg_graph_build(b200_pcg* s) {
 void b200_pcg_graph_destroy(b200_pcg* s) {
   if (s->graph_exec) cudaGraphExecDestroy((cudaGraphExec_t)s->graph_exec);
   if (s->graph) cudaGraphDestroy((cudaGraph_t)s->graph);
-  cudaFree(s->d_args);
-  cudaFree(s->d_run);
-  cudaFree(s->d_gred);
+  dev_free(s->d_args);
+  dev_free(s->d_run);
+  dev_free(s->d_gred);
   s->graph_exec = s->graph = nullptr;
   s->d_args = nullptr; s->d_run = nullptr; s->d_gred = nullptr;
 }

@@ -273,6 +273,110 @@ int b200_vec_bounds_type(int* iseq, const T* l, const T* u, T tol, T infval, int
   return changed > 0.0 ? 1 : 0;
 }
 
+// ------------------------------------------------------------- fused termination-check reductions
+namespace {
+
+struct ResArgs {
+  const T *x, *y, *z, *Ax, *Px, *Aty, *q, *l, *u, *Einv, *Dinv;
+  T infval, deadzone;
+  int n, m;
+};
+
+__device__ __forceinline__ bool res_is_sum(int s) {
+  return s == B200_RES_SC || s == B200_RES_XPX || s == B200_RES_QX;
+}
+
+__global__ void __launch_bounds__(kBlock) residuals_kernel(ResArgs a, double* partials, unsigned* ticket,
+                                                           double* out) {
+  __shared__ double sh[33];
+  __shared__ bool is_last;
+  double v[B200_RES_COUNT];
+#pragma unroll
+  for (int s = 0; s < B200_RES_COUNT; s++) v[s] = 0.0;
+  const int stride = gridDim.x * blockDim.x;
+  const int gtid = blockIdx.x * blockDim.x + threadIdx.x;
+  for (int j = gtid; j < a.m; j += stride) {
+    const double Ax = a.Ax[j], z = a.z[j], e = a.Einv ? (double)a.Einv[j] : 1.0;
+    const double d = Ax - z;
+    v[B200_RES_PRIM_S] = fmax(v[B200_RES_PRIM_S], dabs(d));
+    v[B200_RES_PRIM_U] = fmax(v[B200_RES_PRIM_U], dabs(e * d));
+    v[B200_RES_Z_S]    = fmax(v[B200_RES_Z_S], dabs(z));
+    v[B200_RES_Z_U]    = fmax(v[B200_RES_Z_U], dabs(e * z));
+    v[B200_RES_AX_S]   = fmax(v[B200_RES_AX_S], dabs(Ax));
+    v[B200_RES_AX_U]   = fmax(v[B200_RES_AX_U], dabs(e * Ax));
+    // support function of [l, u] at y projected on the polar recession cone and dead-zoned
+    // (compute_obj_val_dual_gap, auxil.c:245-259)
+    const double lo = a.l[j], hi = a.u[j];
+    double yp = a.y[j];
+    if (hi > +(double)a.infval) {
+      if (lo < -(double)a.infval) yp = 0.0;
+      else yp = (yp < 0.0) ? yp : 0.0;
+    } else if (lo < -(double)a.infval) {
+      yp = (yp > 0.0) ? yp : 0.0;
+    }
+    if (dabs(yp) < (double)a.deadzone) yp = 0.0;
+    v[B200_RES_SC] += hi * (yp > 0.0 ? yp : 0.0) + lo * (yp < 0.0 ? yp : 0.0);
+  }
+  for (int i = gtid; i < a.n; i += stride) {
+    const double q = a.q[i], Px = a.Px[i], Aty = a.m > 0 ? (double)a.Aty[i] : 0.0;
+    const double dv = a.Dinv ? (double)a.Dinv[i] : 1.0, x = a.x[i];
+    double r = q + Px;
+    if (a.m > 0) r += Aty;
+    v[B200_RES_DUAL_S] = fmax(v[B200_RES_DUAL_S], dabs(r));
+    v[B200_RES_DUAL_U] = fmax(v[B200_RES_DUAL_U], dabs(dv * r));
+    v[B200_RES_Q_S]    = fmax(v[B200_RES_Q_S], dabs(q));
+    v[B200_RES_Q_U]    = fmax(v[B200_RES_Q_U], dabs(dv * q));
+    v[B200_RES_PX_S]   = fmax(v[B200_RES_PX_S], dabs(Px));
+    v[B200_RES_PX_U]   = fmax(v[B200_RES_PX_U], dabs(dv * Px));
+    v[B200_RES_ATY_S]  = fmax(v[B200_RES_ATY_S], dabs(Aty));
+    v[B200_RES_ATY_U]  = fmax(v[B200_RES_ATY_U], dabs(dv * Aty));
+    v[B200_RES_XPX] += Px * x;
+    v[B200_RES_QX]  += q * x;
+  }
+#pragma unroll
+  for (int s = 0; s < B200_RES_COUNT; s++) {
+    const double r = res_is_sum(s) ? block_sum(v[s], sh) : block_max(v[s], sh);
+    if (threadIdx.x == 0) partials[s * gridDim.x + blockIdx.x] = r;
+  }
+  if (threadIdx.x == 0) {
+    __threadfence();
+    const unsigned t = atomicAdd(ticket, 1u);
+    is_last = (t == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (is_last) {
+    __threadfence();
+    for (int s = 0; s < B200_RES_COUNT; s++) {
+      double acc = 0.0;
+      for (int b = threadIdx.x; b < gridDim.x; b += blockDim.x) {
+        const double p = __ldcg(&partials[s * gridDim.x + b]);
+        acc = res_is_sum(s) ? acc + p : fmax(acc, p);
+      }
+      acc = res_is_sum(s) ? block_sum(acc, sh) : block_max(acc, sh);
+      if (threadIdx.x == 0) out[s] = acc;
+    }
+    if (threadIdx.x == 0) *ticket = 0;
+  }
+}
+
+}  // namespace
+
+extern "C" void b200_admm_residuals(const T* x, const T* y, const T* z, const T* Ax, const T* Px,
+                                    const T* Aty, const T* q, const T* l, const T* u, const T* Einv,
+                                    const T* Dinv, T infval, T deadzone, int n, int m, double* h_out) {
+  Context& c = ctx();
+  ResArgs a{x, y, z, Ax, Px, Aty, q, l, u, Einv, Dinv, infval, deadzone, n, m};
+  const int nm = n > m ? n : m;
+  int grid = ew_grid(nm);
+  if (grid > kMaxRedBlocks) grid = kMaxRedBlocks;
+  residuals_kernel<<<grid, kBlock, 0, c.stream>>>(a, c.d_partials, c.d_ticket, c.d_scalar);
+  count_launch();
+  B200_CHECK(cudaMemcpyAsync(c.h_scalar, c.d_scalar, sizeof(double) * B200_RES_COUNT,
+                             cudaMemcpyDeviceToHost, c.stream));
+  B200_CHECK(cudaStreamSynchronize(c.stream));
+  for (int s = 0; s < B200_RES_COUNT; s++) h_out[s] = c.h_scalar[s];
+}
+
 // ------------------------------------------------------------- fused ADMM steps
 // compute_rhs (src/auxil.c:136-158): x~ = sigma x_prev - q ; z~ = z_prev - rho^-1 y
 void b200_admm_compute_rhs(T* xt, T* zt, const T* x_prev, const T* q, const T* z_prev, const T* y,
