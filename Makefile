@@ -21,7 +21,7 @@ CFLAGS  := -O3 -fPIC -std=gnu11 -w -DNDEBUG
 CINC    := -Ialgebra/b200/config -Ialgebra/b200 -Iinclude \
            -I$(REF)/include/public -I$(REF)/include/private
 
-CU_SRC   := $(CSRC)/context.cu $(CSRC)/vec_kernels.cu $(CSRC)/csr.cu $(CSRC)/pcg.cu $(CSRC)/pcg_graph.cu
+CU_SRC   := $(CSRC)/context.cu $(CSRC)/vec_kernels.cu $(CSRC)/csr.cu $(CSRC)/pcg.cu $(CSRC)/pcg_graph.cu $(CSRC)/dist.cu
 CU_HDR   := $(CSRC)/common.cuh $(CSRC)/csr.cuh $(CSRC)/pcg.cuh include/osqp_b200.h
 CORE_SRC := $(addprefix $(REF)/src/,auxil.c error.c scaling.c util.c osqp_api.c polish.c timing_linux.c)
 ALG_SRC  := $(wildcard algebra/b200/*.c)
@@ -34,11 +34,11 @@ kernels: $(LIBDIR)/libb200_kernels_f64.so $(LIBDIR)/libb200_kernels_f32.so
 
 $(LIBDIR)/libb200_kernels_f64.so: $(CU_SRC) $(CU_HDR)
 	@mkdir -p $(LIBDIR)
-	$(NVCC) $(NVFLAGS) -shared -o $@ $(CU_SRC) -cudart static
+	$(NVCC) $(NVFLAGS) -shared -o $@ $(CU_SRC) -cudart static -ldl
 
 $(LIBDIR)/libb200_kernels_f32.so: $(CU_SRC) $(CU_HDR)
 	@mkdir -p $(LIBDIR)
-	$(NVCC) $(NVFLAGS) -DB200_USE_FLOAT -shared -o $@ $(CU_SRC) -cudart static
+	$(NVCC) $(NVFLAGS) -DB200_USE_FLOAT -shared -o $@ $(CU_SRC) -cudart static -ldl
 
 # auxil.c is compiled from the reference tree UNCHANGED, with four of its functions renamed on the
 # command line so that algebra/b200/fused_admm.c can provide the fused versions (see that file)

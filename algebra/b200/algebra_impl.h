@@ -45,6 +45,18 @@ struct OSQPMatrix_ {
 };
 
 /*
+ * Row-sharded multi-GPU mode (one process per GPU).  The core runs unchanged
+ * and identically on every rank; the backend is told the global column count n and the local row
+ * count m_local once (osqp_b200_dist_configure, before osqp_setup) and from then on treats every
+ * vector of length m_local as ROW-SHARDED (its reductions are combined across ranks) and every
+ * other vector as replicated.  m_local must differ from n so that the classification is
+ * unambiguous; the partitioner guarantees it.
+ */
+extern OSQPInt b200_dist_n;
+extern OSQPInt b200_dist_mlocal;
+#define B200_IS_SHARDED(len) (b200_dist_mlocal >= 0 && (len) == b200_dist_mlocal && b200_dist_world() > 1)
+
+/*
  * Scalar cache: the fused termination check (fused_admm.c) computes every norm the core asks for
  * right afterwards (compute_prim_tol / compute_dual_tol / compute_rho_estimate, src/auxil.c:14-47,
  * 334-458) in one kernel and parks them here keyed by (weight pointer, vector pointer).  An entry is

@@ -6,6 +6,7 @@
 #include "osqp.h"
 #include "types.h"
 #include "pcg_interface.h"
+#include "algebra_impl.h"
 
 /* total CG iterations and number of linear solves of this solver (synchronises) */
 OSQPInt osqp_b200_cg_stats(const OSQPSolver* solver, long long* total_iters, long long* n_solves) {
@@ -35,4 +36,13 @@ OSQPInt osqp_b200_sizeof(OSQPInt which) {
   case 4: return (OSQPInt)sizeof(OSQPInt);
   default: return -1;
   }
+}
+
+/* Declare the row-sharded layout before osqp_setup: n = global number of variables, m_local =
+ * rows of A held by this rank (must differ from n).  m_local < 0 switches the mode off. */
+OSQPInt osqp_b200_dist_configure(OSQPInt n, OSQPInt m_local) {
+  if (m_local >= 0 && m_local == n) return 1;
+  b200_dist_n      = n;
+  b200_dist_mlocal = m_local;
+  return 0;
 }

@@ -384,6 +384,22 @@ void OSQPMatrix_Axpy(const OSQPMatrix* A, const OSQPVectorf* x, OSQPVectorf* y, 
 void OSQPMatrix_Atxpy(const OSQPMatrix* A, const OSQPVectorf* x, OSQPVectorf* y, OSQPFloat alpha,
                       OSQPFloat beta) {
   if (y->length <= 0) return;
+  if (!A->is_symmetric && b200_dist_world() > 1 && b200_dist_mlocal >= 0) {
+    /* row-sharded A: A'x = sum over ranks of A_r' x_r -> one all-reduce of the length-n result.
+       beta y must be added once, after the exchange. */
+    if (beta == 0.0) {
+      b200_csr_spmv(A->St, x->d_val, y->d_val, alpha, 0.0);
+      b200_dist_allreduce_sum(y->d_val, (int)y->length);
+    } else {
+      OSQPFloat* tmp = (OSQPFloat*)b200_malloc((size_t)y->length * sizeof(OSQPFloat));
+      if (!tmp) return;
+      b200_csr_spmv(A->St, x->d_val, tmp, alpha, 0.0);
+      b200_dist_allreduce_sum(tmp, (int)y->length);
+      b200_vec_add_scaled(y->d_val, 1.0, tmp, beta, y->d_val, (int)y->length);
+      b200_free(tmp);
+    }
+    return;
+  }
   b200_csr_spmv(A->is_symmetric ? A->S : A->St, x->d_val, y->d_val, alpha, beta);
 }
 
@@ -396,7 +412,11 @@ void OSQPMatrix_col_norm_inf(const OSQPMatrix* M, OSQPVectorf* E) {
      (algebra/cuda/matrix.cu:136-140).  The builtin backend is the parity oracle, so the Ruiz
      scaling (scaling.c:38) follows it. */
   if (M->is_symmetric) b200_csr_row_absmax_lower(M->S, E->d_val);
-  else                 b200_csr_row_absmax(M->St, E->d_val);
+  else {
+    b200_csr_row_absmax(M->St, E->d_val);
+    /* row-sharded A: a column's norm is the max over the ranks' row blocks */
+    if (b200_dist_world() > 1 && b200_dist_mlocal >= 0) b200_dist_allreduce_max(E->d_val, (int)E->length);
+  }
 }
 
 void OSQPMatrix_row_norm_inf(const OSQPMatrix* M, OSQPVectorf* E) {

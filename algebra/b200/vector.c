@@ -232,6 +232,21 @@ void OSQPVectorf_set_scalar_if_gt(OSQPVectorf* x, const OSQPVectorf* z, OSQPFloa
 /* ------------------------------------------------------------------ reductions
  * each returns a host scalar by value and is therefore one stream synchronisation */
 
+OSQPInt b200_dist_n      = -1;
+OSQPInt b200_dist_mlocal = -1;
+
+/* reductions over row-sharded vectors are combined across ranks inside the kernel library */
+#define DIST_REDUCE(len, expr)                  \
+  do {                                          \
+    if (B200_IS_SHARDED(len)) {                 \
+      b200_dist_scope(1);                       \
+      expr;                                     \
+      b200_dist_scope(0);                       \
+    } else {                                    \
+      expr;                                     \
+    }                                           \
+  } while (0)
+
 static b200_norm_cache g_cache;
 
 void b200_norm_cache_reset(void) { g_cache.count = 0; g_cache.epoch = 0; }
@@ -262,41 +277,60 @@ int b200_norm_cache_get(const void* s, const void* v, OSQPFloat* val) {
 OSQPFloat OSQPVectorf_norm_inf(const OSQPVectorf* v) {
   OSQPFloat cached;
   if (b200_norm_cache_get(OSQP_NULL, v->d_val, &cached)) return cached;
-  return b200_vec_norm_inf(v->d_val, v->length);
+  DIST_REDUCE(v->length, cached = b200_vec_norm_inf(v->d_val, v->length));
+  return cached;
 }
 
 OSQPFloat OSQPVectorf_scaled_norm_inf(const OSQPVectorf* S, const OSQPVectorf* v) {
   OSQPFloat cached;
   if (b200_norm_cache_get(S->d_val, v->d_val, &cached)) return cached;
-  return b200_vec_scaled_norm_inf(S->d_val, v->d_val, v->length);
+  DIST_REDUCE(v->length, cached = b200_vec_scaled_norm_inf(S->d_val, v->d_val, v->length));
+  return cached;
 }
 
 OSQPFloat OSQPVectorf_norm_inf_diff(const OSQPVectorf* a, const OSQPVectorf* b) {
-  return b200_vec_norm_inf_diff(a->d_val, b->d_val, a->length);
+  OSQPFloat r;
+  DIST_REDUCE(a->length, r = b200_vec_norm_inf_diff(a->d_val, b->d_val, a->length));
+  return r;
 }
 
-OSQPFloat OSQPVectorf_norm_1(const OSQPVectorf* a) { return b200_vec_norm_1(a->d_val, a->length); }
+OSQPFloat OSQPVectorf_norm_1(const OSQPVectorf* a) {
+  OSQPFloat r;
+  DIST_REDUCE(a->length, r = b200_vec_norm_1(a->d_val, a->length));
+  return r;
+}
 
 OSQPFloat OSQPVectorf_norm_2(const OSQPVectorf* a) { return b200_vec_norm_2(a->d_val, a->length); }
 
 OSQPFloat OSQPVectorf_dot_prod(const OSQPVectorf* a, const OSQPVectorf* b) {
-  return b200_vec_dot(a->d_val, b->d_val, a->length);
+  OSQPFloat r;
+  DIST_REDUCE(a->length, r = b200_vec_dot(a->d_val, b->d_val, a->length));
+  return r;
 }
 
 OSQPFloat OSQPVectorf_dot_prod_signed(const OSQPVectorf* a, const OSQPVectorf* b, OSQPInt sign) {
-  return b200_vec_dot_signed(a->d_val, b->d_val, (int)sign, a->length);
+  OSQPFloat r;
+  DIST_REDUCE(a->length, r = b200_vec_dot_signed(a->d_val, b->d_val, (int)sign, a->length));
+  return r;
 }
 
 OSQPInt OSQPVectorf_all_leq(const OSQPVectorf* l, const OSQPVectorf* u) {
-  return b200_vec_all_leq(l->d_val, u->d_val, l->length);
+  OSQPInt r;
+  DIST_REDUCE(l->length, r = b200_vec_all_leq(l->d_val, u->d_val, l->length));
+  return r;
 }
 
 OSQPInt OSQPVectorf_in_reccone(const OSQPVectorf* y, const OSQPVectorf* l, const OSQPVectorf* u,
                                OSQPFloat infval, OSQPFloat tol) {
-  return b200_vec_in_reccone(y->d_val, l->d_val, u->d_val, infval, tol, y->length);
+  OSQPInt r;
+  DIST_REDUCE(y->length, r = b200_vec_in_reccone(y->d_val, l->d_val, u->d_val, infval, tol, y->length));
+  return r;
 }
 
 OSQPInt OSQPVectorf_ew_bounds_type(OSQPVectori* iseq, const OSQPVectorf* l, const OSQPVectorf* u,
                                    OSQPFloat tol, OSQPFloat infval) {
-  return b200_vec_bounds_type(iseq->d_val, l->d_val, u->d_val, tol, infval, iseq->length);
+  OSQPInt r;
+  DIST_REDUCE(iseq->length,
+              r = b200_vec_bounds_type(iseq->d_val, l->d_val, u->d_val, tol, infval, iseq->length));
+  return r;
 }

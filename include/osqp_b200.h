@@ -218,6 +218,25 @@ void b200_admm_residuals(const b200_float* d_x, const b200_float* d_y, const b20
                          const b200_float* d_q, const b200_float* d_l, const b200_float* d_u,
                          const b200_float* d_Einv, const b200_float* d_Dinv, b200_float infval,
                          b200_float deadzone, int n, int m, double* h_out);
+/* ------------------------------------------------------ row-sharded multi-GPU mode
+ * One process per GPU.  Every rank holds a block of ROWS of A (and the matching slices of the
+ * m-vectors); n-vectors and P are replicated.  The only data-path exchange is one all-reduce of
+ * a length-n vector per K.p (and per A'y).  New functionality: the reference has no multi-GPU
+ * path.  NCCL is loaded lazily; the 128-byte unique id is created on rank
+ * 0 and distributed by the host program (torch.distributed in bench.py / tests). */
+int  b200_dist_unique_id(unsigned char* id128);
+int  b200_dist_init(int rank, int world, const unsigned char* id128);   /* after b200_init */
+void b200_dist_finalize(void);
+int  b200_dist_world(void);
+int  b200_dist_rank(void);
+/* while the scope is 1, the scalar-returning reductions combine their result across ranks (max or
+ * sum as appropriate) before handing it to the host: set by the backend around reductions over
+ * row-sharded vectors */
+void b200_dist_scope(int sharded);
+void b200_dist_allreduce_sum(b200_float* d_buf, int n);   /* in place, library stream */
+void b200_dist_allreduce_max(b200_float* d_buf, int n);
+void b200_dist_stats(unsigned long long* n_calls, unsigned long long* bytes);
+
 /* bumped by every kernel launch / device copy of the library: lets the backend cache scalars and
  * know when they went stale */
 unsigned long long b200_epoch(void);

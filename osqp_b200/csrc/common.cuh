@@ -78,6 +78,11 @@ inline int ew_grid(long long n) {
   return (int)(want < cap ? want : cap);
 }
 
+// dist.cu
+bool dist_active();
+bool dist_scope();
+void dist_allreduce_f64(double* d_buf, int n, bool is_max);
+
 // ------------------------------------------------------------------ device side
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll

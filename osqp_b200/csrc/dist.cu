@@ -1,0 +1,141 @@
+// dist.cu -- row-sharded multi-GPU mode: one process per GPU, NCCL over NVLink/NVSwitch for the one
+// exchange step the path has (the length-n partial K p, and A'y in the residual check).
+//
+// The reference has no multi-GPU path at all; this is new functionality specified
+// by BASELINE.json north_star / SURVEY.md section 8e.  NCCL is dlopen'ed so that the single-GPU
+// library has no dependency on it; in a torch process the already-loaded libnccl.so.2 is reused.
+#include "common.cuh"
+
+#include <dlfcn.h>
+#include <cstring>
+
+using namespace b200;
+
+namespace {
+
+typedef void* nccl_comm_t;
+struct nccl_uid { char internal[128]; };
+typedef int (*fn_get_uid)(nccl_uid*);
+typedef int (*fn_init_rank)(nccl_comm_t*, int, nccl_uid, int);
+typedef int (*fn_allreduce)(const void*, void*, size_t, int, int, nccl_comm_t, cudaStream_t);
+typedef int (*fn_destroy)(nccl_comm_t);
+typedef const char* (*fn_errstr)(int);
+
+struct Dist {
+  void* lib = nullptr;
+  fn_get_uid get_uid = nullptr;
+  fn_init_rank init_rank = nullptr;
+  fn_allreduce allreduce = nullptr;
+  fn_destroy destroy = nullptr;
+  fn_errstr errstr = nullptr;
+  nccl_comm_t comm = nullptr;
+  int rank = 0, world = 1, scope = 0;
+  unsigned long long n_allreduce = 0, bytes_allreduce = 0;
+};
+Dist g;
+
+constexpr int NCCL_FLOAT = 7, NCCL_DOUBLE = 8;   // ncclFloat32 / ncclFloat64 (nccl.h ncclDataType_t)
+constexpr int NCCL_SUM = 0, NCCL_MAX = 2;        // ncclRedOp_t
+
+bool load_nccl() {
+  if (g.lib) return true;
+  const char* names[] = {"libnccl.so.2", "libnccl.so"};
+  for (const char* nm : names) {
+    g.lib = dlopen(nm, RTLD_NOW | RTLD_GLOBAL);
+    if (g.lib) break;
+  }
+  if (!g.lib) {
+    fprintf(stderr, "[osqp_b200] cannot dlopen libnccl.so.2: %s\n", dlerror());
+    return false;
+  }
+  g.get_uid   = (fn_get_uid)dlsym(g.lib, "ncclGetUniqueId");
+  g.init_rank = (fn_init_rank)dlsym(g.lib, "ncclCommInitRank");
+  g.allreduce = (fn_allreduce)dlsym(g.lib, "ncclAllReduce");
+  g.destroy   = (fn_destroy)dlsym(g.lib, "ncclCommDestroy");
+  g.errstr    = (fn_errstr)dlsym(g.lib, "ncclGetErrorString");
+  return g.get_uid && g.init_rank && g.allreduce && g.destroy;
+}
+
+bool nccl_ok(int rc, const char* what) {
+  if (rc == 0) return true;
+  fprintf(stderr, "[osqp_b200] NCCL error %d (%s) in %s\n", rc, g.errstr ? g.errstr(rc) : "?", what);
+  if (!ctx().last_error) ctx().last_error = 10000 + rc;
+  return false;
+}
+
+}  // namespace
+
+namespace b200 {
+// used by the reductions in vec_kernels.cu: combine a device scalar block across ranks when the
+// backend declared the operand row-sharded
+bool dist_active() { return g.comm != nullptr && g.world > 1; }
+bool dist_scope() { return dist_active() && g.scope; }
+void dist_allreduce_f64(double* d_buf, int n, bool is_max) {
+  if (!dist_active() || n <= 0) return;
+  nccl_ok(g.allreduce(d_buf, d_buf, (size_t)n, NCCL_DOUBLE, is_max ? NCCL_MAX : NCCL_SUM, g.comm,
+                      ctx().stream), "ncclAllReduce(f64)");
+  g.n_allreduce++;
+  g.bytes_allreduce += (unsigned long long)n * 8;
+}
+}  // namespace b200
+
+extern "C" {
+
+int b200_dist_unique_id(unsigned char* id128) {
+  if (!load_nccl()) return 1;
+  nccl_uid u;
+  if (!nccl_ok(g.get_uid(&u), "ncclGetUniqueId")) return 1;
+  memcpy(id128, u.internal, 128);
+  return 0;
+}
+
+int b200_dist_init(int rank, int world, const unsigned char* id128) {
+  if (world <= 1) { g.rank = 0; g.world = 1; return 0; }
+  if (!load_nccl()) return 1;
+  if (g.comm) return 0;
+  nccl_uid u;
+  memcpy(u.internal, id128, 128);
+  if (!nccl_ok(g.init_rank(&g.comm, world, u, rank), "ncclCommInitRank")) return 1;
+  g.rank = rank;
+  g.world = world;
+  return 0;
+}
+
+void b200_dist_finalize(void) {
+  if (g.comm) {
+    cudaStreamSynchronize(ctx().stream);
+    g.destroy(g.comm);
+    g.comm = nullptr;
+  }
+  g.world = 1;
+  g.rank = 0;
+}
+
+int b200_dist_world(void) { return g.world; }
+int b200_dist_rank(void) { return g.rank; }
+void b200_dist_scope(int sharded) { g.scope = sharded; }
+
+void b200_dist_allreduce_sum(T* d_buf, int n) {
+  if (!dist_active() || n <= 0) return;
+  ctx().epoch++;
+  nccl_ok(g.allreduce(d_buf, d_buf, (size_t)n, sizeof(T) == 8 ? NCCL_DOUBLE : NCCL_FLOAT, NCCL_SUM, g.comm,
+                      ctx().stream), "ncclAllReduce(sum)");
+  g.n_allreduce++;
+  g.bytes_allreduce += (unsigned long long)n * sizeof(T);
+}
+
+void b200_dist_allreduce_max(T* d_buf, int n) {
+  if (!dist_active() || n <= 0) return;
+  ctx().epoch++;
+  nccl_ok(g.allreduce(d_buf, d_buf, (size_t)n, sizeof(T) == 8 ? NCCL_DOUBLE : NCCL_FLOAT, NCCL_MAX, g.comm,
+                      ctx().stream), "ncclAllReduce(max)");
+  g.n_allreduce++;
+  g.bytes_allreduce += (unsigned long long)n * sizeof(T);
+}
+
+void b200_dist_stats(unsigned long long* n_calls, unsigned long long* bytes) {
+  if (n_calls) *n_calls = g.n_allreduce;
+  if (bytes) *bytes = g.bytes_allreduce;
+}
+
+}  // extern "C"

@@ -236,7 +236,7 @@ __global__ void k2_rowptr_kernel(int n, const int* rpP, const int* rpAt, int* rp
 }
 
 // one warp per row: copy P row (sigma added on the diagonal) then A' row (columns shifted by n)
-__global__ void __launch_bounds__(kBlock) k2_fill_kernel(int n, T sigma, const int* rpP, const int* ciP,
+__global__ void __launch_bounds__(kBlock) k2_fill_kernel(int n, T sigma, T pscale, const int* rpP, const int* ciP,
                                                          const T* vP, const int* rpAt, const int* ciAt,
                                                          const T* vAt, const int* rp, int* ci, T* v) {
   const int lane = threadIdx.x & 31;
@@ -247,7 +247,7 @@ __global__ void __launch_bounds__(kBlock) k2_fill_kernel(int n, T sigma, const i
     for (int k = s0 + lane; k < e0; k += 32) {
       const int c = ciP[k];
       ci[dst + k - s0] = c;
-      v[dst + k - s0]  = vP[k] + (c == row ? sigma : (T)0);
+      v[dst + k - s0]  = pscale * (vP[k] + (c == row ? sigma : (T)0));
     }
     dst += e0 - s0;
     if (rpAt) {
@@ -327,6 +327,11 @@ b200_pcg* b200_pcg_create(const b200_csr* P, const b200_csr* A, const b200_csr* 
   // also the structure a row-sharded solve needs: kernel boundaries where the all-reduce goes)
   const char* env = getenv("B200_PCG_DRIVER");
   s->use_graph = env ? (strcmp(env, "graph") == 0) : 0;
+  if (dist_active()) {
+    s->sharded   = 1;
+    s->use_graph = 1;                       // shares the lean kernels and device structs
+    s->include_P = (b200_dist_rank() == 0);
+  }
   if (s->use_graph && b200_pcg_graph_build(s) != 0) {
     fprintf(stderr, "[osqp_b200] graph PCG driver unavailable, using the persistent kernel\n");
     b200_pcg_graph_destroy(s);
@@ -363,7 +368,7 @@ void b200_pcg_refresh_matrices(b200_pcg* s) {
   int cap  = c.sm_count * 8;
   if (grid > cap) grid = cap;
   k2_fill_kernel<<<grid, kBlock, 0, c.stream>>>(
-      n, s->sigma, s->P->d_row_ptr, s->P->d_col_ind, s->P->d_val, hasA ? s->At->d_row_ptr : nullptr,
+      n, s->sigma, (T)(s->include_P ? 1 : 0), s->P->d_row_ptr, s->P->d_col_ind, s->P->d_val, hasA ? s->At->d_row_ptr : nullptr,
       hasA ? s->At->d_col_ind : nullptr, hasA ? s->At->d_val : nullptr, s->K2.d_row_ptr,
       s->K2.d_col_ind, s->K2.d_val);
   count_launch();
@@ -375,6 +380,11 @@ void b200_pcg_refresh_precond(b200_pcg* s) {
   const int n = s->n;
   if (n <= 0) return;
   if (s->m > 0 && s->precond) b200_csr_row_wsumsq(s->At, s->d_rho_vec, s->rho, s->d_ad);
+  // row-sharded: diag(A' R A) = sum over ranks of the local column sums
+  if (s->sharded && s->precond) {
+    if (s->m <= 0) B200_CHECK(cudaMemsetAsync(s->d_ad, 0, sizeof(T) * n, c.stream));
+    b200_dist_allreduce_sum(s->d_ad, n);
+  }
   precond_kernel<<<ew_grid(n), kBlock, 0, c.stream>>>(n, s->sigma, s->d_pd, s->d_ad, s->d_minv, s->precond);
   count_launch();
 }
@@ -407,6 +417,7 @@ int b200_pcg_solve(b200_pcg* s, T* d_b, int admm_iter, double prim_res, double d
   a.reduction_threshold = reduction_threshold;
   a.prim_res = prim_res; a.dual_res = dual_res; a.tol_fraction = tol_fraction;
   a.st = s->d_state; a.red = s->d_red;
+  if (s->sharded) return b200_pcg_sharded_solve(s, a);
   if (s->use_graph) return b200_pcg_graph_solve(s, a);
   void* args[] = {&a};
   bool ok = B200_CHECK(cudaLaunchCooperativeKernel((const void*)pcg_kernel, dim3(s->grid), dim3(kSpmvBlock),

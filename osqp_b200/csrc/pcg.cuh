@@ -67,8 +67,10 @@ struct b200_pcg {
   b200::PcgState* d_state = nullptr;
   double*   d_red   = nullptr;
   int grid = 1, max_grid = 1;
-  // graph driver
+  // graph driver / row-sharded driver
   int use_graph = 0;
+  int sharded = 0;       // row-sharded multi-GPU mode (dist.cu)
+  int include_P = 1;     // sharded: only rank 0 carries P + sigma I in the fused operator
   b200::PcgArgs* d_args = nullptr;
   b200::PcgRun*  d_run  = nullptr;
   double*        d_gred = nullptr;     // SLOT_COUNT * gred_stride partials
@@ -81,4 +83,5 @@ struct b200_pcg {
 int  b200_pcg_graph_build(b200_pcg* s);
 void b200_pcg_graph_destroy(b200_pcg* s);
 int  b200_pcg_graph_solve(b200_pcg* s, const b200::PcgArgs& a);
+int  b200_pcg_sharded_solve(b200_pcg* s, const b200::PcgArgs& a);
 void b200_pcg_graph_configure_kernels();

@@ -157,6 +157,8 @@ __global__ void __launch_bounds__(kSpmvBlock, B200_SPMV_MINBLOCKS) g_pass_A(cons
 // pass over the fused operator [P + sigma I | A'].
 //   MODE 0: P2  r = K2 [x; t] - b1 ; p = -M^-1 r ; totals r'y, ||r||_inf -> run
 //   MODE 1: L2  Kp = K2 [p; t] ; total p'Kp -> run
+//   MODE 2/3 (row-sharded): Kp = this rank's PARTIAL K2 [x; t] / K2 [p; t]; the all-reduce and
+//           the scalars follow in separate kernels (g_resid_init / g_dot_pKp)
 template <int MODE>
 __global__ void __launch_bounds__(kSpmvBlock, B200_SPMV_MINBLOCKS) g_pass_K(const PcgArgs* ap, PcgRun* run, double* red,
                                                        int stride) {
@@ -165,7 +167,7 @@ __global__ void __launch_bounds__(kSpmvBlock, B200_SPMV_MINBLOCKS) g_pass_K(cons
   const PcgArgs& a = *ap;
   Pipe pipe = pipe_init(dsm);
   const int n = a.n;
-  const T* src = (MODE == 0) ? a.x : a.p;
+  const T* src = (MODE == 0 || MODE == 2) ? a.x : a.p;
   const T* t = a.t;
   const T* b1 = a.b;
   const T* minv = a.minv;
@@ -182,11 +184,14 @@ __global__ void __launch_bounds__(kSpmvBlock, B200_SPMV_MINBLOCKS) g_pass_K(cons
           p[row] = -yy;
           acc0 += (double)rr * (double)yy;
           acc1 = fmax(acc1, fabs((double)rr));
-        } else {
+        } else if (MODE == 1) {
           Kp[row] = s;
           acc0 += (double)p[row] * (double)s;
+        } else {
+          Kp[row] = s;
         }
       });
+  if (MODE >= 2) return;
   double tot;
   if (MODE == 0) {
     acc0 = block_sum(acc0, shr);
@@ -207,6 +212,78 @@ __global__ void __launch_bounds__(kSpmvBlock, B200_SPMV_MINBLOCKS) g_pass_K(cons
       run->pKp = tot;
       run->ticket[SLOT_PKP] = 0;
     }
+  }
+}
+
+// row-sharded: Kp[i] = (A_r' t)_i partial, for the ||rhs|| of the tolerance
+__global__ void __launch_bounds__(kSpmvBlock, B200_SPMV_MINBLOCKS) g_pass_At(const PcgArgs* ap) {
+  extern __shared__ __align__(128) unsigned char dsm[];
+  const PcgArgs& a = *ap;
+  Pipe pipe = pipe_init(dsm);
+  const T* t = a.t;
+  T* Kp = a.Kp;
+  spmv_pass<SumOp>(
+      a.At, blockIdx.x, gridDim.x, pipe, [&](int, int c, T v) { return v * t[c]; },
+      [&](int row, T s) { Kp[row] = s; });
+}
+
+// row-sharded: ||b1 + Kp||_inf -> run->rhs_norm   (Kp = all-reduced A'(rho .* b2))
+__global__ void __launch_bounds__(kBlock) g_rhs_norm_sum(const PcgArgs* ap, PcgRun* run, double* red,
+                                                         int stride, int have_At) {
+  __shared__ double shr[33];
+  const PcgArgs& a = *ap;
+  double mx = 0.0;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < a.n; i += gridDim.x * blockDim.x)
+    mx = fmax(mx, fabs((double)(a.b[i] + (have_At ? a.Kp[i] : (T)0))));
+  mx = block_max(mx, shr);
+  double tot;
+  if (publish<true>(mx, red, stride, SLOT_RHS, &run->ticket[SLOT_RHS], true, shr, tot) && threadIdx.x == 0) {
+    run->rhs_norm = tot;
+    run->ticket[SLOT_RHS] = 0;
+  }
+}
+
+// row-sharded P2 tail: r = Kp - b1 ; p = -M^-1 r ; totals r'y, ||r||_inf (n-vectors are replicated,
+// so every rank computes the same totals and no scalar exchange is needed)
+__global__ void __launch_bounds__(kBlock) g_resid_init(const PcgArgs* ap, PcgRun* run, double* red,
+                                                       int stride) {
+  __shared__ double shr[33];
+  const PcgArgs& a = *ap;
+  double acc0 = 0.0, acc1 = 0.0;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < a.n; i += gridDim.x * blockDim.x) {
+    const T rr = a.Kp[i] - a.b[i];
+    const T yy = a.minv[i] * rr;
+    a.r[i] = rr;
+    a.p[i] = -yy;
+    acc0 += (double)rr * (double)yy;
+    acc1 = fmax(acc1, fabs((double)rr));
+  }
+  acc0 = block_sum(acc0, shr);
+  acc1 = block_max(acc1, shr);
+  double tot;
+  publish<true>(acc1, red, stride, SLOT_RMAX, nullptr, false, shr, tot);
+  if (publish<false>(acc0, red, stride, SLOT_RTY, &run->ticket[SLOT_RTY], true, shr, tot)) {
+    const double rmax = fold<true>(red, stride, SLOT_RMAX, shr);
+    if (threadIdx.x == 0) {
+      run->rTy = tot;
+      run->rnorm = rmax;
+      run->ticket[SLOT_RTY] = 0;
+    }
+  }
+}
+
+// row-sharded L2 tail: p'Kp of the all-reduced Kp
+__global__ void __launch_bounds__(kBlock) g_dot_pKp(const PcgArgs* ap, PcgRun* run, double* red, int stride) {
+  __shared__ double shr[33];
+  const PcgArgs& a = *ap;
+  double acc = 0.0;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < a.n; i += gridDim.x * blockDim.x)
+    acc += (double)a.p[i] * (double)a.Kp[i];
+  acc = block_sum(acc, shr);
+  double tot;
+  if (publish<false>(acc, red, stride, SLOT_PKP, &run->ticket[SLOT_PKP], true, shr, tot) && threadIdx.x == 0) {
+    run->pKp = tot;
+    run->ticket[SLOT_PKP] = 0;
   }
 }
 
@@ -246,7 +323,7 @@ __global__ void __launch_bounds__(kBlock) g_update(const PcgArgs* ap, PcgRun* ru
       run->rnorm = rmax;
       run->it   += 1;
       run->ticket[SLOT_RTY] = 0;
-      cudaGraphSetConditional(h, (rmax > run->eps && run->it < a.max_iter) ? 1u : 0u);
+      if (h) cudaGraphSetConditional(h, (rmax > run->eps && run->it < a.max_iter) ? 1u : 0u);
     }
   }
 }
@@ -296,6 +373,9 @@ void b200_pcg_graph_configure_kernels() {
   b200_enable_spmv_smem(g_pass_A<1>);
   b200_enable_spmv_smem(g_pass_K<0>);
   b200_enable_spmv_smem(g_pass_K<1>);
+  b200_enable_spmv_smem(g_pass_K<2>);
+  b200_enable_spmv_smem(g_pass_K<3>);
+  b200_enable_spmv_smem(g_pass_At);
 }
 
 int b200_pcg_graph_build(b200_pcg* s) {
@@ -307,6 +387,7 @@ int b200_pcg_graph_build(b200_pcg* s) {
   ok &= B200_CHECK(dev_malloc(&s->d_gred, sizeof(double) * SLOT_COUNT * s->gred_stride));
   if (!ok) return 1;
   B200_CHECK(cudaMemsetAsync(s->d_run, 0, sizeof(PcgRun), c.stream));
+  if (s->sharded) return 0;   // host-driven loop with an all-reduce per iteration: no graph
 
   cudaGraph_t g = nullptr;
   if (!B200_CHECK(cudaGraphCreate(&g, 0))) return 1;
@@ -414,6 +495,78 @@ int b200_pcg_graph_solve(b200_pcg* s, const PcgArgs& a) {
   count_launch();
   const int nm = n > m ? n : m;
   g_epilogue<<<ew_grid(nm), kBlock, 0, st>>>(d_args, s->d_run);
+  count_launch();
+  return ok ? 0 : 1;
+}
+
+// ------------------------------------------------------------------ row-sharded driver
+// Every rank holds a row block A_r (CSR), A_r' and the matching slices of the m-vectors; x, p, r,
+// Kp, M^-1 are replicated.  K p = (P + sigma I) p [rank 0 only] + A_r' (rho .* (A_r p)) summed by ONE
+// NCCL all-reduce of the length-n partial per CG iteration; all CG scalars are then computed
+// redundantly from replicated vectors, so they are bit-identical on every rank and the ranks take
+// the same branch without any scalar exchange.  The loop is driven by the host, which reads
+// (||r||_inf, eps, it) back once per iteration.
+int b200_pcg_sharded_solve(b200_pcg* s, const PcgArgs& a) {
+  Context& c = ctx();
+  cudaStream_t st = c.stream;
+  const int cap = s->gred_stride;
+  const int n = s->n, m = s->m;
+  const int gn = ew_grid(n) < cap ? ew_grid(n) : cap;
+  g_set_args<<<1, 32, 0, st>>>(s->d_args, a);
+  count_launch();
+  const PcgArgs* d_args = s->d_args;
+  PcgRun* run = s->d_run;
+  cudaGraphConditionalHandle none = 0;
+
+  if (a.polishing || a.admm_iter == 1) {
+    if (m > 0) {
+      g_rhs_t<<<ew_grid(m), kBlock, 0, st>>>(d_args);
+      count_launch();
+      g_pass_At<<<pass_grid(*s->At, cap), kSpmvBlock, kSpmvSmemBytes, st>>>(d_args);
+      count_launch();
+    } else {
+      B200_CHECK(cudaMemsetAsync(s->d_Kp, 0, sizeof(T) * n, st));
+    }
+    b200_dist_allreduce_sum(s->d_Kp, n);
+    g_rhs_norm_sum<<<gn, kBlock, 0, st>>>(d_args, run, s->d_gred, cap, 1);
+    count_launch();
+  }
+  g_tolerance<<<1, 32, 0, st>>>(d_args, run);
+  count_launch();
+  if (m > 0) {
+    if (a.ax_valid) g_p1_carried<<<ew_grid(m), kBlock, 0, st>>>(d_args);
+    else g_pass_A<0><<<pass_grid(*s->A, cap), kSpmvBlock, kSpmvSmemBytes, st>>>(d_args);
+    count_launch();
+  }
+  g_pass_K<2><<<pass_grid(s->K2, cap), kSpmvBlock, kSpmvSmemBytes, st>>>(d_args, run, s->d_gred, cap);
+  count_launch();
+  b200_dist_allreduce_sum(s->d_Kp, n);
+  g_resid_init<<<gn, kBlock, 0, st>>>(d_args, run, s->d_gred, cap);
+  count_launch();
+
+  PcgRun h;
+  bool ok = true;
+  for (;;) {
+    ok &= B200_CHECK(cudaMemcpyAsync(&h, run, sizeof(PcgRun), cudaMemcpyDeviceToHost, st));
+    ok &= B200_CHECK(cudaStreamSynchronize(st));
+    if (!ok || !(h.rnorm > h.eps && h.it < a.max_iter)) break;
+    if (m > 0) {
+      g_pass_A<1><<<pass_grid(*s->A, cap), kSpmvBlock, kSpmvSmemBytes, st>>>(d_args);
+      count_launch();
+    }
+    g_pass_K<3><<<pass_grid(s->K2, cap), kSpmvBlock, kSpmvSmemBytes, st>>>(d_args, run, s->d_gred, cap);
+    count_launch();
+    b200_dist_allreduce_sum(s->d_Kp, n);
+    g_dot_pKp<<<gn, kBlock, 0, st>>>(d_args, run, s->d_gred, cap);
+    count_launch();
+    const int nm = n > m ? n : m;
+    g_update<<<ew_grid(nm) < cap ? ew_grid(nm) : cap, kBlock, 0, st>>>(d_args, run, s->d_gred, cap, none);
+    count_launch();
+    g_direction<<<ew_grid(n), kBlock, 0, st>>>(d_args, run);
+    count_launch();
+  }
+  const int nm = n > m ? n : m;
+  g_epilogue<<<ew_grid(nm), kBlock, 0, st>>>(d_args, run);
   count_launch();
   return ok ? 0 : 1;
 }

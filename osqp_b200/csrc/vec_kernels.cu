@@ -76,12 +76,13 @@ __global__ void __launch_bounds__(kBlock) reduce_kernel(int n, F f, double* part
 
 template <int OP, class F>
 inline double run_reduce(int n, F f) {
-  if (n <= 0) return 0.0;
+  if (n <= 0 && !dist_scope()) return 0.0;
   Context& c = ctx();
   int grid = ew_grid(n);
   if (grid > kMaxRedBlocks) grid = kMaxRedBlocks;
   reduce_kernel<OP><<<grid, kBlock, 0, c.stream>>>(n, f, c.d_partials, c.d_ticket, c.d_scalar);
   count_launch();
+  if (dist_scope()) dist_allreduce_f64(c.d_scalar, 1, OP == RED_MAX);   // row-sharded operand
   B200_CHECK(cudaMemcpyAsync(c.h_scalar, c.d_scalar, sizeof(double), cudaMemcpyDeviceToHost, c.stream));
   B200_CHECK(cudaStreamSynchronize(c.stream));
   return c.h_scalar[0];
@@ -371,6 +372,12 @@ extern "C" void b200_admm_residuals(const T* x, const T* y, const T* z, const T*
   if (grid > kMaxRedBlocks) grid = kMaxRedBlocks;
   residuals_kernel<<<grid, kBlock, 0, c.stream>>>(a, c.d_partials, c.d_ticket, c.d_scalar);
   count_launch();
+  if (dist_active()) {
+    // slots 0..5 are maxima over the row-sharded m-vectors, slot 6 (support function) a sum over
+    // them; the n-vector slots are replicated and identical on every rank
+    dist_allreduce_f64(c.d_scalar + B200_RES_PRIM_S, B200_RES_SC - B200_RES_PRIM_S, true);
+    dist_allreduce_f64(c.d_scalar + B200_RES_SC, 1, false);
+  }
   B200_CHECK(cudaMemcpyAsync(c.h_scalar, c.d_scalar, sizeof(double) * B200_RES_COUNT,
                              cudaMemcpyDeviceToHost, c.stream));
   B200_CHECK(cudaStreamSynchronize(c.stream));

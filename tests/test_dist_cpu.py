@@ -1,0 +1,82 @@
+"""CPU tests of the N > 1 paths (gloo, world_size 2): row partitioning of the sharded mode, the
+unique-id hand-off used to build the NCCL communicator, and the rank bookkeeping of bench.py."""
+import os
+import subprocess
+import sys
+import textwrap
+
+import numpy as np
+import pytest
+import scipy.sparse as sp
+
+from conftest import ROOT
+from osqp_b200 import problems
+from osqp_b200.dist import partition_rows, shard_problem
+
+
+@pytest.mark.parametrize("world", [1, 2, 3, 4, 8])
+def test_partition_covers_rows_and_balances_nonzeros(world):
+    pb = problems.lasso(40, 400, density=0.1, seed=2)
+    A = sp.csr_matrix(pb["A"])
+    n = A.shape[1]
+    b = partition_rows(A, world)
+    assert b[0] == 0 and b[-1] == A.shape[0] and (np.diff(b) > 0).all()
+    if world > 1:      # only the sharded mode needs block lengths to differ from n
+        assert not (np.diff(b) == n).any()
+    nnz = np.array([A[b[r]:b[r + 1]].nnz for r in range(world)])
+    assert nnz.max() <= 1.6 * nnz.mean() + n
+    # the shards reassemble to the original problem
+    parts = [shard_problem(pb, r, world) for r in range(world)]
+    assert (sp.vstack([p["A"] for p in parts]) != sp.csc_matrix(pb["A"])).nnz == 0
+    assert np.array_equal(np.concatenate([p["l"] for p in parts]), pb["l"])
+    assert np.array_equal(np.concatenate([p["u"] for p in parts]), pb["u"])
+
+
+def test_partition_avoids_blocks_of_exactly_n_rows():
+    A = sp.random(20, 10, density=0.3, format="csr", random_state=0)   # m = 2n: the even split hits n
+    b = partition_rows(A, 2)
+    assert not (np.diff(b) == 10).any() and b[-1] == 20
+
+
+WORKER = textwrap.dedent("""
+    import os, sys
+    sys.path.insert(0, {root!r})
+    import numpy as np, torch, torch.distributed as dist
+    from osqp_b200 import problems
+    from osqp_b200.dist import exchange_unique_id, shard_problem
+    dist.init_process_group("gloo")
+    rank, world = dist.get_rank(), dist.get_world_size()
+    uid = exchange_unique_id(lambda: bytes(range(128)), dist)
+    assert uid == bytes(range(128)), "unique id not identical on every rank"
+    pb = problems.portfolio(300, 20, density=0.2, seed=1)
+    sh = shard_problem(pb, rank, world)
+    rows = torch.tensor([sh["A"].shape[0], sh["A"].nnz], dtype=torch.int64)
+    dist.all_reduce(rows)
+    assert rows[0].item() == pb["A"].shape[0] and rows[1].item() == pb["A"].nnz
+    # max-over-ranks timing reduction used by bench.py
+    t = torch.tensor([float(rank + 1)], dtype=torch.float64)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    assert t.item() == world
+    dist.barrier()
+    if rank == 0:
+        print("WORKER_OK")
+    dist.destroy_process_group()
+""")
+
+
+def test_gloo_world_size_2(tmp_path):
+    script = tmp_path / "worker.py"
+    script.write_text(WORKER.format(root=str(ROOT)))
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1")
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                          "--master-addr", "127.0.0.1", "--master-port", "29533", str(script)],
+                         capture_output=True, text=True, env=env, timeout=300)
+    assert "WORKER_OK" in out.stdout, out.stdout[-2000:] + out.stderr[-2000:]
+
+
+def test_bench_reference_arm_other_ranks_exit_quietly():
+    """--impl reference under torchrun: only rank 0 works and prints"""
+    env = dict(os.environ, RANK="1", WORLD_SIZE="2", LOCAL_RANK="1")
+    out = subprocess.run([sys.executable, str(ROOT / "bench.py"), "--impl", "reference", "--gpus", "2",
+                          "--steps", "1", "--warmup", "1"], capture_output=True, text=True, env=env, timeout=120)
+    assert out.returncode == 0 and out.stdout.strip() == ""
