@@ -37,7 +37,7 @@ namespace b200 {
 #define B200_SPMV_TILE 2048
 #endif
 #ifndef B200_SPMV_MINBLOCKS
-#define B200_SPMV_MINBLOCKS 1
+#define B200_SPMV_MINBLOCKS 4   /* caps the pass kernels at 64 registers (ptxas takes 94 unbounded) */
 #endif
 #ifndef B200_PCG_MINBLOCKS
 #define B200_PCG_MINBLOCKS 4

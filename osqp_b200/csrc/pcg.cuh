@@ -70,6 +70,7 @@ struct b200_pcg {
   // graph driver / row-sharded driver
   int use_graph = 0;
   int sharded = 0;       // row-sharded multi-GPU mode (dist.cu)
+  int lean = 0;          // loop body uses the flat 32-register passes
   int include_P = 1;     // sharded: only rank 0 carries P + sigma I in the fused operator
   b200::PcgArgs* d_args = nullptr;
   b200::PcgRun*  d_run  = nullptr;

@@ -16,6 +16,7 @@
 #include "pcg.cuh"
 
 #include <cstring>
+#include <vector>
 
 using namespace b200;
 
@@ -80,10 +81,11 @@ __global__ void __launch_bounds__(kSpmvBlock, B200_SPMV_MINBLOCKS) g_rhs_norm(co
   Pipe pipe = pipe_init(dsm);
   const T* b1 = a.b;
   const T* t = a.t;
+  const CsrView M = a.At;   // local copy: the argument block lives in global memory
   double mx = 0.0;
   if (a.m > 0) {
     spmv_pass<SumOp>(
-        a.At, blockIdx.x, gridDim.x, pipe, [&](int, int c, T v) { return v * t[c]; },
+        M, blockIdx.x, gridDim.x, pipe, [&](int, int c, T v) { return v * t[c]; },
         [&](int row, T s) { mx = fmax(mx, fabs((double)(b1[row] + s))); });
   } else {
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < a.n; i += gridDim.x * blockDim.x)
@@ -145,8 +147,9 @@ __global__ void __launch_bounds__(kSpmvBlock, B200_SPMV_MINBLOCKS) g_pass_A(cons
   const T rho = a.rho;
   T* t = a.t;
   T* out = (MODE == 0) ? a.Ax : a.w;
+  const CsrView M = a.A;    // local copy: the argument block lives in global memory
   spmv_pass<SumOp>(
-      a.A, blockIdx.x, gridDim.x, pipe, [&](int, int c, T v) { return v * src[c]; },
+      M, blockIdx.x, gridDim.x, pipe, [&](int, int c, T v) { return v * src[c]; },
       [&](int row, T s) {
         out[row] = s;
         const T rr = rho_vec ? rho_vec[row] : rho;
@@ -173,8 +176,9 @@ __global__ void __launch_bounds__(kSpmvBlock, B200_SPMV_MINBLOCKS) g_pass_K(cons
   const T* minv = a.minv;
   T* r = a.r; T* p = a.p; T* Kp = a.Kp;
   double acc0 = 0.0, acc1 = 0.0;
+  const CsrView M = a.K2;   // local copy: the argument block lives in global memory
   spmv_pass<SumOp>(
-      a.K2, blockIdx.x, gridDim.x, pipe,
+      M, blockIdx.x, gridDim.x, pipe,
       [&](int, int c, T v) { return v * (c < n ? src[c] : t[c - n]); },
       [&](int row, T s) {
         if (MODE == 0) {
@@ -222,8 +226,9 @@ __global__ void __launch_bounds__(kSpmvBlock, B200_SPMV_MINBLOCKS) g_pass_At(con
   Pipe pipe = pipe_init(dsm);
   const T* t = a.t;
   T* Kp = a.Kp;
+  const CsrView M = a.At;
   spmv_pass<SumOp>(
-      a.At, blockIdx.x, gridDim.x, pipe, [&](int, int c, T v) { return v * t[c]; },
+      M, blockIdx.x, gridDim.x, pipe, [&](int, int c, T v) { return v * t[c]; },
       [&](int row, T s) { Kp[row] = s; });
 }
 
@@ -285,6 +290,99 @@ __global__ void __launch_bounds__(kBlock) g_dot_pKp(const PcgArgs* ap, PcgRun* r
     run->pKp = tot;
     run->ticket[SLOT_PKP] = 0;
   }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Lean passes for the CG loop body (matrices without over-long rows): the same CSR-stream tile as
+// spmv_pass, written out flat -- one CTA of 512 threads per 2048-entry tile, a single batch of 4
+// (col, val, gather) chains per thread, no long-row branch, no generic functors -- so that ptxas
+// keeps it at 32 registers (full occupancy).  Measured on the Lasso matrix: 58 us per pass against
+// 73-80 us for the generic instantiation (tools/micro/spmv_variants.cu).
+//   MODE 0: L1   w = A p ; t = rho .* w
+//   MODE 1: L2   Kp = [P + sigma I | A'] [p; t] ; total p'Kp -> run
+constexpr int kLeanBlock = 512;
+static_assert(kTile == 4 * kLeanBlock, "lean pass assumes one batch of 4 per thread");
+
+template <int MODE>
+__global__ void __launch_bounds__(kLeanBlock, 3) g_lean_pass(const PcgArgs* ap, PcgRun* run, double* red,
+                                                             int stride) {
+  __shared__ T sm[kTile];
+  __shared__ int srp[kMaxRows + 1];
+  __shared__ double shr[33];
+  const PcgArgs& a = *ap;
+  // everything the tile needs is pulled out of the (global-memory) argument block once
+  const int* __restrict__ row_ptr = (MODE == 0) ? a.A.row_ptr : a.K2.row_ptr;
+  const int* __restrict__ col_ind = (MODE == 0) ? a.A.col_ind : a.K2.col_ind;
+  const T* __restrict__   val     = (MODE == 0) ? a.A.val : a.K2.val;
+  const int4* __restrict__ desc   = (MODE == 0) ? a.A.desc : a.K2.desc;
+  const T* __restrict__ p = a.p;
+  const T* __restrict__ t = a.t;
+  const T* __restrict__ rho_vec = a.rho_vec;
+  const T rho = a.rho;
+  T* __restrict__ out0 = (MODE == 0) ? a.w : a.Kp;
+  T* __restrict__ out1 = a.t;
+  const int n = a.n;
+  const int tid = threadIdx.x;
+  const int4 d = __ldg(desc + blockIdx.x);
+  const int nnz0 = d.z, cnt = d.w, nrows = d.y & 0xffffff, lg = d.y >> 24;
+  for (int i = tid; i <= nrows; i += kLeanBlock) srp[i] = ld_stream(row_ptr + d.x + i) - nnz0;
+  int c[4];
+  T   v[4];
+#pragma unroll
+  for (int u = 0; u < 4; u++) {
+    const int k = u * kLeanBlock + tid;
+    if (k < cnt) {
+      c[u] = ld_stream(col_ind + nnz0 + k);
+      v[u] = ld_stream(val + nnz0 + k);
+    }
+  }
+#pragma unroll
+  for (int u = 0; u < 4; u++) {
+    const int k = u * kLeanBlock + tid;
+    if (k < cnt) {
+      if (MODE == 0) sm[k] = v[u] * p[c[u]];
+      else sm[k] = v[u] * (c[u] < n ? p[c[u]] : t[c[u] - n]);
+    }
+  }
+  __syncthreads();
+  const int g = 1 << lg, gid = tid >> lg, lig = tid & (g - 1), ngroup = kLeanBlock >> lg;
+  double acc = 0.0;
+  for (int base = 0; base < nrows; base += ngroup) {   // one trip except for tiles of 1-2 entry rows
+    const int r = base + gid;
+    T sum = 0;
+    if (r < nrows) {
+      const int e = srp[r + 1];
+      for (int k = srp[r] + lig; k < e; k += g) sum += sm[k];
+    }
+    for (int o = g >> 1; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    if (r < nrows && lig == 0) {
+      const int row = d.x + r;
+      if (MODE == 0) {
+        out0[row] = sum;
+        out1[row] = (rho_vec ? rho_vec[row] : rho) * sum;
+      } else {
+        out0[row] = sum;
+        acc += (double)p[row] * (double)sum;
+      }
+    }
+  }
+  if (MODE == 1) {
+    acc = block_sum(acc, shr);
+    double tot;
+    if (publish<false>(acc, red, stride, SLOT_PKP, &run->ticket[SLOT_PKP], true, shr, tot) &&
+        threadIdx.x == 0) {
+      run->pKp = tot;
+      run->ticket[SLOT_PKP] = 0;
+    }
+  }
+}
+
+// the flat kernel does not handle chunks of over-long rows
+static bool lean_ok(const b200_csr& M, const std::vector<int4>& desc) {
+  if (M.nlong > 0) return false;
+  for (const int4& d : desc)
+    if (d.y < 0) return false;
+  return true;
 }
 
 // first node of the loop graph: arm the WHILE condition from the initial residual
@@ -382,6 +480,8 @@ int b200_pcg_graph_build(b200_pcg* s) {
   Context& c = ctx();
   bool ok = true;
   s->gred_stride = c.sm_count * 32;
+  if (s->K2.nblocks + 8 > s->gred_stride) s->gred_stride = s->K2.nblocks + 8;
+  if (s->A && s->A->nblocks + 8 > s->gred_stride) s->gred_stride = s->A->nblocks + 8;
   ok &= B200_CHECK(dev_malloc(&s->d_args, sizeof(PcgArgs)));
   ok &= B200_CHECK(dev_malloc(&s->d_run, sizeof(PcgRun)));
   ok &= B200_CHECK(dev_malloc(&s->d_gred, sizeof(double) * SLOT_COUNT * s->gred_stride));
@@ -430,13 +530,37 @@ int b200_pcg_graph_build(b200_pcg* s) {
     prev = node;
   };
   const int cap = s->gred_stride;
+  // lean flat kernels when neither matrix has over-long rows (checked on the host schedules)
+  bool lean = getenv("B200_PCG_NO_LEAN") == nullptr;
+  if (lean) {
+    auto fetch = [&](const b200_csr& M) {
+      std::vector<int4> h(M.nblocks > 0 ? M.nblocks : 0);
+      if (M.nblocks > 0) {
+        B200_CHECK(cudaMemcpyAsync(h.data(), M.d_desc, sizeof(int4) * M.nblocks, cudaMemcpyDeviceToHost, c.stream));
+        B200_CHECK(cudaStreamSynchronize(c.stream));
+      }
+      return h;
+    };
+    lean = lean_ok(s->K2, fetch(s->K2)) && (s->m == 0 || lean_ok(*s->A, fetch(*s->A))) &&
+           s->K2.nblocks <= cap && (s->m == 0 || s->A->nblocks <= cap);
+  }
+  s->lean = lean ? 1 : 0;
+  if (getenv("B200_TRACE_SETUP"))
+    fprintf(stderr, "[b200 trace] graph PCG driver: %s passes, K2 tiles %d, A tiles %d, partial stride %d\n",
+            lean ? "lean" : "generic", s->K2.nblocks, s->m > 0 ? s->A->nblocks : 0, cap);
   if (s->m > 0) {
-    void* a1[] = {(void*)&d_args};
-    add((void*)g_pass_A<1>, dim3(pass_grid(*s->A, cap)), dim3(kSpmvBlock), kSpmvSmemBytes, a1);
+    if (lean) {
+      void* a1[] = {(void*)&d_args, (void*)&d_run, (void*)&d_red, (void*)&stride};
+      add((void*)g_lean_pass<0>, dim3(s->A->nblocks), dim3(kLeanBlock), 0, a1);
+    } else {
+      void* a1[] = {(void*)&d_args};
+      add((void*)g_pass_A<1>, dim3(pass_grid(*s->A, cap)), dim3(kSpmvBlock), kSpmvSmemBytes, a1);
+    }
   }
   {
     void* a2[] = {(void*)&d_args, (void*)&d_run, (void*)&d_red, (void*)&stride};
-    add((void*)g_pass_K<1>, dim3(pass_grid(s->K2, cap)), dim3(kSpmvBlock), kSpmvSmemBytes, a2);
+    if (lean) add((void*)g_lean_pass<1>, dim3(s->K2.nblocks), dim3(kLeanBlock), 0, a2);
+    else add((void*)g_pass_K<1>, dim3(pass_grid(s->K2, cap)), dim3(kSpmvBlock), kSpmvSmemBytes, a2);
   }
   {
     void* a3[] = {(void*)&d_args, (void*)&d_run, (void*)&d_red, (void*)&stride, (void*)&h};

@@ -174,10 +174,10 @@ def test_tight_parity_with_builtin_qdldl(b200_lib, oracle_lib, family, rho_is_ve
     """north_star: same status, objective to 1e-6 relative, residuals within eps, iteration count
     within the stated band."""
     pb = _family(family)
-    # eps = 1e-6 is the tightest tolerance an indirect solve can certify: the CG tolerance has the
+    # eps ~ 3e-7 is about the tightest tolerance an indirect solve can certify: the CG tolerance has the
     # hard floor OSQP_CG_TOL_MIN = 1e-7 on the (scaled) linear-system residual, which bounds the
     # reachable dual residual (same in the reference: cuda_pcg_interface.cu:60)
-    EPS = 1e-6
+    EPS = 3e-7
     kw = dict(eps_abs=EPS, eps_rel=EPS, max_iter=20000, rho_is_vec=rho_is_vec, check_termination=25,
               verbose=0)
     so = OSQP(oracle_lib).setup(pb["P"], pb["q"], pb["A"], pb["l"], pb["u"], **kw)
