@@ -36,11 +36,25 @@ CPU_SAMPLE_SCALE = 0.02          # QDLDL fill grows ~ scale^3: 0.02 -> ~6 s, 0.0
 F = 8
 
 
-def make_problem(scale, seed):
+def make_problem(scale, seed, workload="lasso"):
+    """BASELINE.json workloads; `scale` shrinks them proportionally (1.0 = the named size)."""
     from osqp_b200 import problems
-    if scale >= 1.0:
-        return problems.lasso(int(1e5 * scale), int(1e6 * scale), density=1e-4, seed=seed)
-    return problems.lasso(int(1e5 * scale), int(1e6 * scale), density=1e-4 / scale, seed=seed)
+    if workload == "lasso":        # configs[1]
+        if scale >= 1.0:
+            return problems.lasso(int(1e5 * scale), int(1e6 * scale), density=1e-4, seed=seed)
+        return problems.lasso(int(1e5 * scale), int(1e6 * scale), density=1e-4 / scale, seed=seed)
+    if workload == "portfolio":    # configs[2]: k = 1e4 factors, n = 1e6 assets, nnz(F) = 1e8
+        return problems.portfolio(int(1e6 * scale), int(1e4 * min(1.0, scale * 10) if scale < 1 else 1e4),
+                                  density=1e-2, seed=seed)
+    if workload == "huber":        # configs[3]
+        return problems.huber(10_000, int(1e7 * scale), density=1e-3, seed=seed)
+    if workload == "svm":          # configs[3]
+        return problems.svm(10_000, int(1e7 * scale), density=1e-3, seed=seed)
+    if workload == "random_qp":    # configs[0]
+        return problems.random_qp(10_000, 20_000, 200_000, seed=seed)
+    if workload == "mpc":          # configs[4], one instance
+        return problems.mpc(N=12, seed=seed)
+    raise ValueError(workload)
 
 
 def peaks():
@@ -159,7 +173,7 @@ def run_reference(args):
         "e2e": {"value": v, "unit": "iter/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "time_to_solution_ms": 1e3 * total / args.steps, "gpu_launches": 0, "status": status,
     }
-    print(json.dumps(out))
+    args.emit(json.dumps(out))
 
 
 # ------------------------------------------------------------------------------- B200 arm
@@ -226,10 +240,22 @@ def run_b200(args):
     from osqp_b200 import OSQP, problems
     from osqp_b200.devmem import kernels
     prec = args.dtype
-    k = kernels(prec)
-    if k.b200_init(local) != 0:
-        raise RuntimeError("no usable GPU: the B200 backend has no CPU fallback")
-    pb = make_problem(args.scale, seed=1 + rank)
+    sharded = args.mode == "sharded" and world > 1
+    if sharded:
+        # ONE QP, rows of A split over the ranks, one all-reduce of the length-n partial per K.p
+        from osqp_b200.dist import ShardedOSQP, init_sharded
+        k = init_sharded(dist, local, prec)
+        kernels(prec)
+        pb = make_problem(args.scale, seed=1, workload=args.workload)
+        _Base = OSQP
+
+        def OSQP(_prec):  # noqa: N802 -- same constructor signature as the single-GPU class
+            return ShardedOSQP(rank, world, _prec)
+    else:
+        k = kernels(prec)
+        if k.b200_init(local) != 0:
+            raise RuntimeError("no usable GPU: the B200 backend has no CPU fallback")
+        pb = make_problem(args.scale, seed=1 + rank, workload=args.workload)
     n, m = pb["P"].shape[0], pb["A"].shape[0]
     nnzA, nnzP = int(pb["A"].nnz), int(pb["P"].nnz)
 
@@ -297,13 +323,15 @@ def run_b200(args):
         dist.all_reduce(w, op=dist.ReduceOp.SUM)
         ms, e_total = t.tolist()
         iters, e_iters, launches, dcg, dns = w.tolist()
+        if sharded:     # every rank ran the SAME iterations of the one shared QP
+            iters, e_iters, dcg, dns = iters / world, e_iters / world, dcg / world, dns / world
     else:
         dcg, dns = cg1 - cg0, ns1 - ns0
 
     if rank == 0:
         peak, peak_src = peaks()
         kcg = max(1, int(round(dcg / max(dns, 1))))
-        roof = pcg_roofline(k, pb, kcg) if prec == "f64" else None
+        roof = pcg_roofline(k, pb, kcg) if (prec == "f64" and not sharded) else None
         traffic = None
         tp = ROOT / "profiles" / "pcg_traffic.json"
         if tp.exists() and roof is not None:
@@ -332,17 +360,20 @@ def run_b200(args):
         out = {
             "metric": "admm_iters_per_sec", "value": iters / (ms / 1e3), "unit": "iter/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "ms_per_step": ms / args.steps, "higher_is_better": True,
+            "scaling": "strong" if sharded else "weak",
             "vs_baseline": None, "dtype": prec, "data": "synthetic",
-            "config": {"workload": "lasso_1e5x1e6 (BASELINE configs[1])" if args.scale == 1.0 else
-                       f"lasso generator at scale {args.scale}",
+            "config": {"workload": ("lasso_1e5x1e6 (BASELINE configs[1])" if (args.scale == 1.0 and args.workload == "lasso")
+                                    else f"{args.workload} generator at scale {args.scale}"),
                        "n": n, "m": m, "nnzA": nnzA, "nnzP": nnzP, "eps": 1e-3,
                        "solver": "indirect: persistent-kernel Jacobi PCG on the reduced KKT system",
                        "step": "one cold-start osqp_solve to eps 1e-3",
-                       "parallelism": "1 GPU" if world == 1 else f"{world} independent QPs, one per GPU, no comms",
+                       "parallelism": ("1 GPU" if world == 1 else
+                                       (f"one QP row-sharded over {world} GPUs, 1 NCCL all-reduce (n doubles) per K.p"
+                                        if sharded else f"{world} independent QPs, one per GPU, no comms")),
                        "l2_policy": "working set (>=460 MB of matrices per CG iteration) exceeds the 126 MB L2",
                        "settings": {kk: vv for kk, vv in SETTINGS.items()}},
-            "admm_iters_per_step": iters / args.steps / world,
+            "admm_iters_per_step": iters / args.steps / (1 if sharded else world),
             "cg_iters_per_admm_iter": dcg / max(dns, 1),
             "time_to_solution_ms": ms / args.steps,
             "status": status, "obj_val": obj,
@@ -360,10 +391,33 @@ def run_b200(args):
                                "bytes_per_launch": roof["bytes_per_launch"],
                                "ms_per_launch": roof["ms_per_launch"]}
         out["cpu_baseline"] = cpu
-        print(json.dumps(out))
+        args.emit(json.dumps(out))
     if dist is not None:
         dist.barrier()
+        if sharded:
+            k.b200_dist_finalize()
         dist.destroy_process_group()
+
+
+class QuietStdout:
+    """Everything any library writes to fd 1 (NCCL prints its version there) goes to stderr; the one
+    JSON line is written to the real stdout."""
+
+    def __enter__(self):
+        sys.stdout.flush()
+        self.real = os.dup(1)
+        os.dup2(2, 1)
+        self.out = os.fdopen(self.real, "w")
+        return self
+
+    def emit(self, line):
+        self.out.write(line + "\n")
+        self.out.flush()
+
+    def __exit__(self, *exc):
+        sys.stdout.flush()
+        os.dup2(self.real, 1)
+        return False
 
 
 def main():
@@ -375,13 +429,19 @@ def main():
     ap.add_argument("--scale", type=float, default=1.0, help="problem scale (1.0 = BASELINE configs[1])")
     ap.add_argument("--dtype", default="f64", choices=["f64", "f32"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--mode", default="batch", choices=["batch", "sharded"],
+                    help="N > 1: independent QPs per GPU (default, no comms) or ONE row-sharded QP")
+    ap.add_argument("--workload", default="lasso",
+                    choices=["lasso", "portfolio", "huber", "svm", "random_qp", "mpc"])
     args = ap.parse_args()
     if args.warmup < 1:
         args.warmup = 1
-    if args.impl == "reference":
-        run_reference(args)
-    else:
-        run_b200(args)
+    with QuietStdout() as q:
+        args.emit = q.emit
+        if args.impl == "reference":
+            run_reference(args)
+        else:
+            run_b200(args)
 
 
 if __name__ == "__main__":
