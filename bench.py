@@ -11,8 +11,9 @@ value  : iterations / s with the problem resident in HBM (solver set up before t
 e2e    : the same metric through the public API from HOST arrays: every step is osqp_setup
          (host -> device copies of P, A, q, l, u and all format conversions) + osqp_solve + the
          device -> host read of the solution, on the host clock.
-N > 1  : the path shards as independent QPs (BASELINE configs[4] style): every rank solves its own
-         instance (its own seed) with no data-path collective -> "scaling": "weak".
+N > 1  : the path shards as independent QPs (BASELINE configs[4] style): every rank sets up and solves
+         its own instance with no data-path collective -> "scaling": "weak".
+         `--mode sharded` instead solves ONE QP with the rows of A split over the ranks (strong).
 --impl reference : the reference's own CPU path (unmodified core + builtin backend + QDLDL
          restatement = oracle/_ref/libosqp_builtin.so) on a bounded sample of the same generator.
 """
@@ -255,7 +256,9 @@ def run_b200(args):
         k = kernels(prec)
         if k.b200_init(local) != 0:
             raise RuntimeError("no usable GPU: the B200 backend has no CPU fallback")
-        pb = make_problem(args.scale, seed=1 + rank, workload=args.workload)
+        # same generator and seed on every rank: per-GPU work is identical, which is what "weak"
+        # scaling compares (each rank still builds, uploads and solves its own copy)
+        pb = make_problem(args.scale, seed=1, workload=args.workload)
     n, m = pb["P"].shape[0], pb["A"].shape[0]
     nnzA, nnzP = int(pb["A"].nnz), int(pb["P"].nnz)
 
@@ -370,7 +373,7 @@ def run_b200(args):
                        "step": "one cold-start osqp_solve to eps 1e-3",
                        "parallelism": ("1 GPU" if world == 1 else
                                        (f"one QP row-sharded over {world} GPUs, 1 NCCL all-reduce (n doubles) per K.p"
-                                        if sharded else f"{world} independent QPs, one per GPU, no comms")),
+                                        if sharded else f"{world} independent QPs (same generator and seed), one per GPU, no comms")),
                        "l2_policy": "working set (>=460 MB of matrices per CG iteration) exceeds the 126 MB L2",
                        "settings": {kk: vv for kk, vv in SETTINGS.items()}},
             "admm_iters_per_step": iters / args.steps / (1 if sharded else world),
