@@ -69,13 +69,20 @@ typedef struct {
   int                count;
   const void*        s[B200_NORM_CACHE_MAX];   /* weight vector data pointer or NULL */
   const void*        v[B200_NORM_CACHE_MAX];
+  size_t             bytes[B200_NORM_CACHE_MAX]; /* extent of v (and of s) */
   OSQPFloat          val[B200_NORM_CACHE_MAX];
 } b200_norm_cache;
 
 void b200_norm_cache_reset(void);
-void b200_norm_cache_put(const void* s, const void* v, OSQPFloat val);
+void b200_norm_cache_put(const void* s, const void* v, OSQPInt length, OSQPFloat val);
 void b200_norm_cache_seal(void);                       /* stamp with the current epoch */
 int  b200_norm_cache_get(const void* s, const void* v, OSQPFloat* val);
+/* Operations of the termination check that are known to write only `dst` (or nothing, dst = NULL)
+ * bracket themselves with these two calls: if the cache was live before the operation and `dst`
+ * overlaps none of the cached vectors, the cache is re-stamped with the new epoch instead of dying.
+ * Any operation that does NOT bracket itself still kills the cache (the safe default). */
+int  b200_norm_cache_live(void);
+void b200_norm_cache_after(int was_live, const void* dst, OSQPInt length);
 
 #ifdef __cplusplus
 }

@@ -148,20 +148,20 @@ void update_info(OSQPSolver* solver, OSQPInt iter, OSQPInt polishing) {
   /* norms the core asks for next, valid until the next kernel or copy */
   b200_norm_cache_reset();
   if (m) {
-    b200_norm_cache_put(OSQP_NULL, work->z->d_val, (OSQPFloat)r[B200_RES_Z_S]);
-    b200_norm_cache_put(OSQP_NULL, work->Ax->d_val, (OSQPFloat)r[B200_RES_AX_S]);
-    b200_norm_cache_put(OSQP_NULL, work->Aty->d_val, (OSQPFloat)r[B200_RES_ATY_S]);
+    b200_norm_cache_put(OSQP_NULL, work->z->d_val, work->z->length, (OSQPFloat)r[B200_RES_Z_S]);
+    b200_norm_cache_put(OSQP_NULL, work->Ax->d_val, work->Ax->length, (OSQPFloat)r[B200_RES_AX_S]);
+    b200_norm_cache_put(OSQP_NULL, work->Aty->d_val, work->Aty->length, (OSQPFloat)r[B200_RES_ATY_S]);
   }
-  b200_norm_cache_put(OSQP_NULL, work->data->q->d_val, (OSQPFloat)r[B200_RES_Q_S]);
-  b200_norm_cache_put(OSQP_NULL, work->Px->d_val, (OSQPFloat)r[B200_RES_PX_S]);
+  b200_norm_cache_put(OSQP_NULL, work->data->q->d_val, work->data->q->length, (OSQPFloat)r[B200_RES_Q_S]);
+  b200_norm_cache_put(OSQP_NULL, work->Px->d_val, work->Px->length, (OSQPFloat)r[B200_RES_PX_S]);
   if (settings->scaling) {
     if (m) {
-      b200_norm_cache_put(work->scaling->Einv->d_val, work->z->d_val, (OSQPFloat)r[B200_RES_Z_U]);
-      b200_norm_cache_put(work->scaling->Einv->d_val, work->Ax->d_val, (OSQPFloat)r[B200_RES_AX_U]);
-      b200_norm_cache_put(work->scaling->Dinv->d_val, work->Aty->d_val, (OSQPFloat)r[B200_RES_ATY_U]);
+      b200_norm_cache_put(work->scaling->Einv->d_val, work->z->d_val, work->z->length, (OSQPFloat)r[B200_RES_Z_U]);
+      b200_norm_cache_put(work->scaling->Einv->d_val, work->Ax->d_val, work->Ax->length, (OSQPFloat)r[B200_RES_AX_U]);
+      b200_norm_cache_put(work->scaling->Dinv->d_val, work->Aty->d_val, work->Aty->length, (OSQPFloat)r[B200_RES_ATY_U]);
     }
-    b200_norm_cache_put(work->scaling->Dinv->d_val, work->data->q->d_val, (OSQPFloat)r[B200_RES_Q_U]);
-    b200_norm_cache_put(work->scaling->Dinv->d_val, work->Px->d_val, (OSQPFloat)r[B200_RES_PX_U]);
+    b200_norm_cache_put(work->scaling->Dinv->d_val, work->data->q->d_val, work->data->q->length, (OSQPFloat)r[B200_RES_Q_U]);
+    b200_norm_cache_put(work->scaling->Dinv->d_val, work->Px->d_val, work->Px->length, (OSQPFloat)r[B200_RES_PX_U]);
   }
   b200_norm_cache_seal();
 }

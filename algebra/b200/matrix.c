@@ -376,8 +376,11 @@ void OSQPMatrix_rmult_diag(OSQPMatrix* A, const OSQPVectorf* R) {
  * that csc_Axpy_sym_triu computes on the CPU (csc_math.c:114-166). */
 void OSQPMatrix_Axpy(const OSQPMatrix* A, const OSQPVectorf* x, OSQPVectorf* y, OSQPFloat alpha,
                      OSQPFloat beta) {
+  int live;
   if (y->length <= 0) return;
+  live = b200_norm_cache_live();
   b200_csr_spmv(A->S, x->d_val, y->d_val, alpha, beta);
+  b200_norm_cache_after(live, y->d_val, y->length);
 }
 
 /* y = alpha A' x + beta y through the stored transpose (no atomics) */
@@ -400,7 +403,11 @@ void OSQPMatrix_Atxpy(const OSQPMatrix* A, const OSQPVectorf* x, OSQPVectorf* y,
     }
     return;
   }
-  b200_csr_spmv(A->is_symmetric ? A->S : A->St, x->d_val, y->d_val, alpha, beta);
+  {
+    int live = b200_norm_cache_live();
+    b200_csr_spmv(A->is_symmetric ? A->S : A->St, x->d_val, y->d_val, alpha, beta);
+    b200_norm_cache_after(live, y->d_val, y->length);
+  }
 }
 
 /* ---------------------------------------------------------------------- norms */

@@ -192,7 +192,9 @@ void OSQPVectorf_add_scaled3(OSQPVectorf* x, OSQPFloat sca, const OSQPVectorf* a
 }
 
 void OSQPVectorf_ew_prod(OSQPVectorf* c, const OSQPVectorf* a, const OSQPVectorf* b) {
+  int live = b200_norm_cache_live();
   b200_vec_ew_prod(c->d_val, a->d_val, b->d_val, c->length);
+  b200_norm_cache_after(live, c->d_val, c->length);
 }
 
 void OSQPVectorf_ew_bound_vec(OSQPVectorf* x, const OSQPVectorf* z, const OSQPVectorf* l,
@@ -202,7 +204,9 @@ void OSQPVectorf_ew_bound_vec(OSQPVectorf* x, const OSQPVectorf* z, const OSQPVe
 
 void OSQPVectorf_project_polar_reccone(OSQPVectorf* y, const OSQPVectorf* l, const OSQPVectorf* u,
                                        OSQPFloat infval) {
+  int live = b200_norm_cache_live();
   b200_vec_project_polar_reccone(y->d_val, l->d_val, u->d_val, infval, y->length);
+  b200_norm_cache_after(live, y->d_val, y->length);
 }
 
 void OSQPVectorf_ew_reciprocal(OSQPVectorf* b, const OSQPVectorf* a) {
@@ -251,13 +255,38 @@ static b200_norm_cache g_cache;
 
 void b200_norm_cache_reset(void) { g_cache.count = 0; g_cache.epoch = 0; }
 
-void b200_norm_cache_put(const void* s, const void* v, OSQPFloat val) {
+void b200_norm_cache_put(const void* s, const void* v, OSQPInt length, OSQPFloat val) {
   if (g_cache.count < B200_NORM_CACHE_MAX) {
-    g_cache.s[g_cache.count]   = s;
-    g_cache.v[g_cache.count]   = v;
-    g_cache.val[g_cache.count] = val;
+    g_cache.s[g_cache.count]     = s;
+    g_cache.v[g_cache.count]     = v;
+    g_cache.bytes[g_cache.count] = (size_t)length * sizeof(OSQPFloat);
+    g_cache.val[g_cache.count]   = val;
     g_cache.count++;
   }
+}
+
+int b200_norm_cache_live(void) { return g_cache.count > 0 && g_cache.epoch == b200_epoch(); }
+
+static int ranges_overlap(const void* a, size_t na, const void* b, size_t nb) {
+  const char* pa = (const char*)a;
+  const char* pb = (const char*)b;
+  return a && b && pa < pb + nb && pb < pa + na;
+}
+
+void b200_norm_cache_after(int was_live, const void* dst, OSQPInt length) {
+  int    i;
+  size_t nb = (size_t)(length > 0 ? length : 0) * sizeof(OSQPFloat);
+  if (!was_live) return;
+  if (dst && nb) {
+    for (i = 0; i < g_cache.count; i++) {
+      if (ranges_overlap(dst, nb, g_cache.v[i], g_cache.bytes[i]) ||
+          ranges_overlap(dst, nb, g_cache.s[i], g_cache.bytes[i])) {
+        g_cache.count = 0;
+        return;
+      }
+    }
+  }
+  g_cache.epoch = b200_epoch();
 }
 
 void b200_norm_cache_seal(void) { g_cache.epoch = b200_epoch(); }
@@ -276,15 +305,19 @@ int b200_norm_cache_get(const void* s, const void* v, OSQPFloat* val) {
 
 OSQPFloat OSQPVectorf_norm_inf(const OSQPVectorf* v) {
   OSQPFloat cached;
+  int       live = b200_norm_cache_live();
   if (b200_norm_cache_get(OSQP_NULL, v->d_val, &cached)) return cached;
   DIST_REDUCE(v->length, cached = b200_vec_norm_inf(v->d_val, v->length));
+  b200_norm_cache_after(live, OSQP_NULL, 0);     /* a reduction writes no vector */
   return cached;
 }
 
 OSQPFloat OSQPVectorf_scaled_norm_inf(const OSQPVectorf* S, const OSQPVectorf* v) {
   OSQPFloat cached;
+  int       live = b200_norm_cache_live();
   if (b200_norm_cache_get(S->d_val, v->d_val, &cached)) return cached;
   DIST_REDUCE(v->length, cached = b200_vec_scaled_norm_inf(S->d_val, v->d_val, v->length));
+  b200_norm_cache_after(live, OSQP_NULL, 0);
   return cached;
 }
 
@@ -304,13 +337,17 @@ OSQPFloat OSQPVectorf_norm_2(const OSQPVectorf* a) { return b200_vec_norm_2(a->d
 
 OSQPFloat OSQPVectorf_dot_prod(const OSQPVectorf* a, const OSQPVectorf* b) {
   OSQPFloat r;
+  int       live = b200_norm_cache_live();
   DIST_REDUCE(a->length, r = b200_vec_dot(a->d_val, b->d_val, a->length));
+  b200_norm_cache_after(live, OSQP_NULL, 0);
   return r;
 }
 
 OSQPFloat OSQPVectorf_dot_prod_signed(const OSQPVectorf* a, const OSQPVectorf* b, OSQPInt sign) {
   OSQPFloat r;
+  int       live = b200_norm_cache_live();
   DIST_REDUCE(a->length, r = b200_vec_dot_signed(a->d_val, b->d_val, (int)sign, a->length));
+  b200_norm_cache_after(live, OSQP_NULL, 0);
   return r;
 }
 
@@ -323,7 +360,9 @@ OSQPInt OSQPVectorf_all_leq(const OSQPVectorf* l, const OSQPVectorf* u) {
 OSQPInt OSQPVectorf_in_reccone(const OSQPVectorf* y, const OSQPVectorf* l, const OSQPVectorf* u,
                                OSQPFloat infval, OSQPFloat tol) {
   OSQPInt r;
+  int     live = b200_norm_cache_live();
   DIST_REDUCE(y->length, r = b200_vec_in_reccone(y->d_val, l->d_val, u->d_val, infval, tol, y->length));
+  b200_norm_cache_after(live, OSQP_NULL, 0);
   return r;
 }
 

@@ -184,6 +184,10 @@ int  b200_pcg_solve(b200_pcg* s, b200_float* d_b, int admm_iter, double prim_res
  * and tolerance of the last solve */
 void b200_pcg_stats(b200_pcg* s, long long* total_iters, long long* n_solves,
                     int* last_iters, double* last_eps, double* last_rnorm);
+/* development aid: CUDA-event timing (microseconds, averaged over `reps` plain launches) of the
+ * kernels of one CG iteration of the most recently created solver (graph driver, lean passes).
+ * Leaves the iterate in an arbitrary state.  Returns 0, or -1 if there is nothing to profile. */
+int  b200_pcg_profile_last(int reps, double* out_us, int nout);
 
 /* ----------------------------------------------------------- fused ADMM steps
  * One kernel each instead of the 16 launches of update_x / update_z / update_y

@@ -15,6 +15,7 @@ namespace b200 {
 constexpr int kBlock        = 256;    // threads per CTA for every kernel in the library
 constexpr int kMaxRedBlocks = 1184;   // 148 SMs x 8 CTAs: upper bound for reduction grids
 constexpr int kScalarSlots  = 32;
+constexpr int kMailSlots    = 32;     // result values; the sequence word lives at index kMailSlots
 
 struct Context {
   int          refcount   = 0;
@@ -27,11 +28,18 @@ struct Context {
   // result scalars: device slot + pinned host mirror
   double*      d_scalar   = nullptr;
   double*      h_scalar   = nullptr;   // pinned
+  // zero-copy result mailbox (mapped pinned memory): the last CTA of a reduction writes the
+  // value(s) and then a sequence number straight into host memory; the host spins on the
+  // sequence number instead of paying cudaMemcpyAsync + cudaStreamSynchronize (~15 us a call)
+  double*      h_mail     = nullptr;   // kMailSlots doubles + 1 sequence word, host view
+  double*      d_mail     = nullptr;   // device view of the same memory
+  unsigned long long mail_seq = 0;
   // staging buffer for host->device index/value uploads is allocated on demand
   int          last_error = 0;
   unsigned long long launches = 0;
   unsigned long long epoch    = 0;   // launches + device copies: anything that may change a vector
   char         name[256]  = {0};
+  int          trace_on   = 0;   // B200_TRACE_FILE: one CUDA event + host timestamp per launch
 };
 
 Context& ctx();
@@ -61,10 +69,14 @@ inline void dev_free(void* p) {
   if (p) cudaFreeAsync(p, ctx().stream);
 }
 
+// launch tracer (context.cu): development aid, active only when B200_TRACE_FILE is set
+void trace_point(const char* tag);
+
 // called after every kernel launch: counts it and records (sticky) launch-configuration errors
-inline void count_launch() {
+inline void count_launch(const char* tag = __builtin_FUNCTION()) {
   ctx().launches++;
   ctx().epoch++;
+  if (ctx().trace_on) trace_point(tag);
   cudaError_t e = cudaPeekAtLastError();
   if (e != cudaSuccess) check(cudaGetLastError(), "kernel launch");
 }
@@ -78,12 +90,23 @@ inline int ew_grid(long long n) {
   return (int)(want < cap ? want : cap);
 }
 
+// context.cu: wait until the device has posted sequence number `seq` in the mailbox.  Returns
+// false (after synchronising the stream) if the stream finished or failed without posting it.
+bool mail_wait(unsigned long long seq);
+
 // dist.cu
 bool dist_active();
 bool dist_scope();
 void dist_allreduce_f64(double* d_buf, int n, bool is_max);
 
 // ------------------------------------------------------------------ device side
+// post `cnt` results + the sequence number into the mapped host mailbox (one thread)
+__device__ __forceinline__ void mail_post(double* mail, const double* vals, int cnt, unsigned long long seq) {
+  for (int i = 0; i < cnt; i++) mail[i] = vals[i];
+  __threadfence_system();
+  *reinterpret_cast<volatile unsigned long long*>(mail + kMailSlots) = seq;
+}
+
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

@@ -5,11 +5,75 @@
 #include "common.cuh"
 
 #include <cstring>
+#include <cstdlib>
+#include <ctime>
+#include <vector>
 
 namespace b200 {
 Context& ctx() {
   static Context c;
   return c;
+}
+
+// ---- launch tracer: after every launch an event is recorded on the library stream together
+// with the host time of the call.  The dump lists, per launch, the device time since the previous
+// launch finished (= idle gap + kernel duration) and the host time since the previous call, which
+// is what separates "the GPU was busy" from "the GPU waited for the host".
+namespace {
+struct TracePoint { cudaEvent_t ev; const char* tag; double host_us; };
+std::vector<TracePoint> g_trace;
+double host_now_us() {
+  timespec ts;
+  clock_gettime(CLOCK_MONOTONIC, &ts);
+  return ts.tv_sec * 1e6 + ts.tv_nsec * 1e-3;
+}
+}  // namespace
+bool mail_wait(unsigned long long seq) {
+  Context& c = ctx();
+  volatile unsigned long long* word = reinterpret_cast<volatile unsigned long long*>(c.h_mail + kMailSlots);
+  for (unsigned spins = 0;; spins++) {
+    if (*word == seq) return true;
+    if ((spins & 0xfff) == 0xfff) {
+      // the stream draining without the word arriving means the kernel failed
+      cudaError_t q = cudaStreamQuery(c.stream);
+      if (q != cudaErrorNotReady) {
+        if (*word == seq) return true;
+        check(q == cudaSuccess ? cudaErrorUnknown : q, "reduction mailbox");
+        cudaStreamSynchronize(c.stream);
+        return false;
+      }
+    }
+#if defined(__x86_64__)
+    __builtin_ia32_pause();
+#endif
+  }
+}
+
+void trace_point(const char* tag) {
+  if (g_trace.size() >= (1u << 17)) return;
+  TracePoint t;
+  if (cudaEventCreate(&t.ev) != cudaSuccess) return;
+  cudaEventRecord(t.ev, ctx().stream);
+  t.tag = tag;
+  t.host_us = host_now_us();
+  g_trace.push_back(t);
+}
+static void trace_dump() {
+  const char* path = getenv("B200_TRACE_FILE");
+  if (!path || g_trace.empty()) return;
+  cudaStreamSynchronize(ctx().stream);
+  FILE* f = fopen(path, "w");
+  if (f) {
+    fprintf(f, "idx,tag,dev_us_since_prev,host_us_since_prev\n");
+    for (size_t i = 1; i < g_trace.size(); i++) {
+      float ms = 0.f;
+      cudaEventElapsedTime(&ms, g_trace[i - 1].ev, g_trace[i].ev);
+      fprintf(f, "%zu,%s,%.2f,%.2f\n", i, g_trace[i].tag, ms * 1e3, g_trace[i].host_us - g_trace[i - 1].host_us);
+    }
+    fclose(f);
+  }
+  for (auto& t : g_trace) cudaEventDestroy(t.ev);
+  g_trace.clear();
 }
 }  // namespace b200
 
@@ -53,6 +117,11 @@ int b200_init(int device) {
   ok &= B200_CHECK(dev_malloc(&c.d_ticket, sizeof(unsigned) * 4));
   ok &= B200_CHECK(dev_malloc(&c.d_scalar, sizeof(double) * kScalarSlots));
   ok &= B200_CHECK(cudaMallocHost(&c.h_scalar, sizeof(double) * kScalarSlots));
+  ok &= B200_CHECK(cudaHostAlloc(&c.h_mail, sizeof(double) * (kMailSlots + 1), cudaHostAllocMapped));
+  if (!ok) return 1;
+  memset(c.h_mail, 0, sizeof(double) * (kMailSlots + 1));
+  ok &= B200_CHECK(cudaHostGetDevicePointer(&c.d_mail, c.h_mail, 0));
+  c.mail_seq = 0;
   if (!ok) return 1;
   B200_CHECK(cudaMemsetAsync(c.d_ticket, 0, sizeof(unsigned) * 4, c.stream));
   B200_CHECK(cudaMemsetAsync(c.d_scalar, 0, sizeof(double) * kScalarSlots, c.stream));
@@ -61,6 +130,7 @@ int b200_init(int device) {
   c.last_error = 0;
   c.launches   = 0;
   c.refcount   = 1;
+  c.trace_on   = getenv("B200_TRACE_FILE") ? 1 : 0;
   return 0;
 }
 
@@ -69,10 +139,13 @@ void b200_shutdown(void) {
   if (c.refcount <= 0) return;
   if (--c.refcount > 0) return;
   cudaStreamSynchronize(c.stream);
+  if (c.trace_on) trace_dump();
   dev_free(c.d_partials);
   dev_free(c.d_ticket);
   dev_free(c.d_scalar);
   cudaFreeHost(c.h_scalar);
+  cudaFreeHost(c.h_mail);
+  c.h_mail = c.d_mail = nullptr;
   cudaStreamDestroy(c.stream);
   c.d_partials = nullptr;
   c.d_ticket   = nullptr;

@@ -337,11 +337,13 @@ b200_pcg* b200_pcg_create(const b200_csr* P, const b200_csr* A, const b200_csr* 
     b200_pcg_graph_destroy(s);
     s->use_graph = 0;
   }
+  b200_pcg_profile_register(s, true);
   return s;
 }
 
 void b200_pcg_destroy(b200_pcg* s) {
   if (!s) return;
+  b200_pcg_profile_register(s, false);
   dev_free(s->d_x); dev_free(s->d_p); dev_free(s->d_Kp); dev_free(s->d_r); dev_free(s->d_t);
   dev_free(s->d_Ax); dev_free(s->d_w);
   dev_free(s->d_minv); dev_free(s->d_pd); dev_free(s->d_ad);

@@ -14,7 +14,7 @@ constexpr double kCgTolMin    = 1e-7;   // OSQP_CG_TOL_MIN    (osqp_api_constant
 constexpr double kCgPolishTol = 1e-5;   // OSQP_CG_POLISH_TOL (osqp_api_constants.h:216)
 constexpr int    kAxResync    = 50;     // solves between exact recomputations of the carried A x
 
-enum { SLOT_RHS = 0, SLOT_RTY = 1, SLOT_RMAX = 2, SLOT_PKP = 3, SLOT_COUNT = 4 };
+enum { SLOT_RHS = 0, SLOT_RTY = 1, SLOT_RMAX = 2, SLOT_PKP = 3, SLOT_RKP = 4, SLOT_KPKP = 5, SLOT_COUNT = 6 };
 
 struct PcgState {
   double    reduction_factor;
@@ -43,7 +43,7 @@ struct PcgArgs {
 
 // running scalars of one solve in the graph driver (device memory)
 struct PcgRun {
-  double   eps, rTy, rnorm, pKp, beta, rhs_norm;
+  double   eps, rTy, rnorm, pKp, beta, rhs_norm, alpha;
   double   rf, eps_prev;
   int      it, zero_iters;
   unsigned ticket[SLOT_COUNT];
@@ -86,3 +86,4 @@ void b200_pcg_graph_destroy(b200_pcg* s);
 int  b200_pcg_graph_solve(b200_pcg* s, const b200::PcgArgs& a);
 int  b200_pcg_sharded_solve(b200_pcg* s, const b200::PcgArgs& a);
 void b200_pcg_graph_configure_kernels();
+void b200_pcg_profile_register(b200_pcg* s, bool alive);

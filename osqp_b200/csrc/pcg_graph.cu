@@ -63,6 +63,20 @@ __global__ void g_set_args(PcgArgs* dst, PcgArgs a) {
   if (threadIdx.x == 0 && blockIdx.x == 0) *dst = a;
 }
 
+// step length and (predicted) direction coefficient of one CG iteration, from the three dots of
+// the fused-operator pass.  beta uses the expansion of r+'M^-1 r+ so that x, r AND p can be
+// updated by ONE vector kernel (no second grid-wide reduction before the direction update); the
+// exactly reduced r+'y of that kernel replaces the prediction as the next iteration's r'y.
+__device__ __forceinline__ void cg_step_scalars(PcgRun* run, double pKp, double rkp, double kpkp) {
+  const double rTy   = run->rTy;
+  const double alpha = rTy / pKp;
+  const double pred  = rTy + alpha * (2.0 * rkp + alpha * kpkp);
+  double beta = pred / rTy;
+  if (!(beta > 0.0)) beta = 0.0;          // cancellation at convergence: restart direction
+  run->alpha = alpha;
+  run->beta  = beta;
+}
+
 // t = rho .* b2   (only for the ||rhs|| of the tolerance at admm_iter == 1 / polishing)
 __global__ void __launch_bounds__(kBlock) g_rhs_t(const PcgArgs* ap) {
   const PcgArgs& a = *ap;
@@ -175,7 +189,7 @@ __global__ void __launch_bounds__(kSpmvBlock, B200_SPMV_MINBLOCKS) g_pass_K(cons
   const T* b1 = a.b;
   const T* minv = a.minv;
   T* r = a.r; T* p = a.p; T* Kp = a.Kp;
-  double acc0 = 0.0, acc1 = 0.0;
+  double acc0 = 0.0, acc1 = 0.0, acc2 = 0.0;
   const CsrView M = a.K2;   // local copy: the argument block lives in global memory
   spmv_pass<SumOp>(
       M, blockIdx.x, gridDim.x, pipe,
@@ -190,7 +204,10 @@ __global__ void __launch_bounds__(kSpmvBlock, B200_SPMV_MINBLOCKS) g_pass_K(cons
           acc1 = fmax(acc1, fabs((double)rr));
         } else if (MODE == 1) {
           Kp[row] = s;
+          const T yk = minv[row] * s;
           acc0 += (double)p[row] * (double)s;
+          acc1 += (double)r[row] * (double)yk;
+          acc2 += (double)s * (double)yk;
         } else {
           Kp[row] = s;
         }
@@ -211,10 +228,18 @@ __global__ void __launch_bounds__(kSpmvBlock, B200_SPMV_MINBLOCKS) g_pass_K(cons
     }
   } else {
     acc0 = block_sum(acc0, shr);
-    if (publish<false>(acc0, red, stride, SLOT_PKP, &run->ticket[SLOT_PKP], true, shr, tot) &&
-        threadIdx.x == 0) {
-      run->pKp = tot;
-      run->ticket[SLOT_PKP] = 0;
+    acc1 = block_sum(acc1, shr);
+    acc2 = block_sum(acc2, shr);
+    publish<false>(acc1, red, stride, SLOT_RKP, nullptr, false, shr, tot);
+    publish<false>(acc2, red, stride, SLOT_KPKP, nullptr, false, shr, tot);
+    if (publish<false>(acc0, red, stride, SLOT_PKP, &run->ticket[SLOT_PKP], true, shr, tot)) {
+      const double rkp  = fold<false>(red, stride, SLOT_RKP, shr);
+      const double kpkp = fold<false>(red, stride, SLOT_KPKP, shr);
+      if (threadIdx.x == 0) {
+        run->pKp = tot;
+        cg_step_scalars(run, tot, rkp, kpkp);
+        run->ticket[SLOT_PKP] = 0;
+      }
     }
   }
 }
@@ -293,88 +318,184 @@ __global__ void __launch_bounds__(kBlock) g_dot_pKp(const PcgArgs* ap, PcgRun* r
 }
 
 // ---------------------------------------------------------------------------------------------
-// Lean passes for the CG loop body (matrices without over-long rows): the same CSR-stream tile as
-// spmv_pass, written out flat -- one CTA of 512 threads per 2048-entry tile, a single batch of 4
-// (col, val, gather) chains per thread, no long-row branch, no generic functors -- so that ptxas
-// keeps it at 32 registers (full occupancy).  Measured on the Lasso matrix: 58 us per pass against
-// 73-80 us for the generic instantiation (tools/micro/spmv_variants.cu).
+// Lean passes (matrices without over-long rows): the same CSR-stream tile as spmv_pass, written
+// out flat -- 512 threads per 2048-entry tile, a single batch of 4 (col, val, gather) chains per
+// thread, no long-row branch, no generic functors (<= 42 registers, 3 CTAs per SM).  The grid is
+// ONE WAVE (3 CTAs per SM) looping over the tiles round-robin: the per-CTA tail -- block
+// reduction of the dot-product partials, publication, ticket -- is then paid 444 times per pass
+// instead of once per tile (6100 times for the Lasso operator), which measured 45 us of a 120 us
+// pass (profiles/r01_phase_profile.md).
 //   MODE 0: L1   w = A p ; t = rho .* w
-//   MODE 1: L2   Kp = [P + sigma I | A'] [p; t] ; total p'Kp -> run
+//   MODE 1: L2   Kp = [P + sigma I | A'] [p; t] ; totals p'Kp, r'M^-1 Kp, Kp'M^-1 Kp -> alpha, beta
+//   MODE 2: P2   r = K2 [x; t] - b1 ; p = -M^-1 r ; totals r'y, ||r||_inf
+//   MODE 3: P1   Ax = A x ; t = rho .* (Ax - b2)       (exact recomputation of the carried product)
+//   MODE 4/5: phase profile only (plain A' t, plain K2 [p; t])
 constexpr int kLeanBlock = 512;
+constexpr int kLeanCtasPerSm = 3;
 static_assert(kTile == 4 * kLeanBlock, "lean pass assumes one batch of 4 per thread");
 
-template <int MODE>
-__global__ void __launch_bounds__(kLeanBlock, 3) g_lean_pass(const PcgArgs* ap, PcgRun* run, double* red,
-                                                             int stride) {
-  __shared__ T sm[kTile];
-  __shared__ int srp[kMaxRows + 1];
-  __shared__ double shr[33];
-  const PcgArgs& a = *ap;
-  // everything the tile needs is pulled out of the (global-memory) argument block once
-  const int* __restrict__ row_ptr = (MODE == 0) ? a.A.row_ptr : a.K2.row_ptr;
-  const int* __restrict__ col_ind = (MODE == 0) ? a.A.col_ind : a.K2.col_ind;
-  const T* __restrict__   val     = (MODE == 0) ? a.A.val : a.K2.val;
-  const int4* __restrict__ desc   = (MODE == 0) ? a.A.desc : a.K2.desc;
-  const T* __restrict__ p = a.p;
-  const T* __restrict__ t = a.t;
-  const T* __restrict__ rho_vec = a.rho_vec;
-  const T rho = a.rho;
-  T* __restrict__ out0 = (MODE == 0) ? a.w : a.Kp;
-  T* __restrict__ out1 = a.t;
-  const int n = a.n;
-  const int tid = threadIdx.x;
-  const int4 d = __ldg(desc + blockIdx.x);
-  const int nnz0 = d.z, cnt = d.w, nrows = d.y & 0xffffff, lg = d.y >> 24;
-  for (int i = tid; i <= nrows; i += kLeanBlock) srp[i] = ld_stream(row_ptr + d.x + i) - nnz0;
-  int c[4];
-  T   v[4];
-#pragma unroll
-  for (int u = 0; u < 4; u++) {
-    const int k = u * kLeanBlock + tid;
-    if (k < cnt) {
-      c[u] = ld_stream(col_ind + nnz0 + k);
-      v[u] = ld_stream(val + nnz0 + k);
-    }
+// sums of three values over the CTA with one pair of barriers; results valid in thread 0
+__device__ __forceinline__ void block_sum3(double& a, double& b, double& c, double* sh /* >= 3*16 */) {
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  a = warp_sum(a); b = warp_sum(b); c = warp_sum(c);
+  if (lane == 0) { sh[w] = a; sh[16 + w] = b; sh[32 + w] = c; }
+  __syncthreads();
+  if (w == 0) {
+    const int nw = blockDim.x >> 5;
+    a = warp_sum(lane < nw ? sh[lane] : 0.0);
+    b = warp_sum(lane < nw ? sh[16 + lane] : 0.0);
+    c = warp_sum(lane < nw ? sh[32 + lane] : 0.0);
   }
+}
+__device__ __forceinline__ void block_sum_max(double& a, double& mx, double* sh) {
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  a = warp_sum(a); mx = warp_max(mx);
+  if (lane == 0) { sh[w] = a; sh[16 + w] = mx; }
+  __syncthreads();
+  if (w == 0) {
+    const int nw = blockDim.x >> 5;
+    a  = warp_sum(lane < nw ? sh[lane] : 0.0);
+    mx = warp_max(lane < nw ? sh[16 + lane] : 0.0);
+  }
+}
+
+// thread 0 publishes up to three partials of this CTA; the last CTA to arrive folds every slot in
+// index order.  Returns true in all threads of that CTA, totals valid in all its threads.
+template <int NSLOT, bool LAST_IS_MAX>
+__device__ __forceinline__ bool publish_fold(const double* part, const int* slots, double* red, int stride,
+                                             unsigned* ticket, double* shr, double* totals) {
+  __shared__ int s_last;
+  if (threadIdx.x == 0) {
 #pragma unroll
-  for (int u = 0; u < 4; u++) {
-    const int k = u * kLeanBlock + tid;
-    if (k < cnt) {
-      if (MODE == 0) sm[k] = v[u] * p[c[u]];
-      else sm[k] = v[u] * (c[u] < n ? p[c[u]] : t[c[u] - n]);
-    }
+    for (int i = 0; i < NSLOT; i++) red[slots[i] * stride + blockIdx.x] = part[i];
+    __threadfence();
+    s_last = (atomicAdd(ticket, 1u) == gridDim.x - 1);
   }
   __syncthreads();
-  const int g = 1 << lg, gid = tid >> lg, lig = tid & (g - 1), ngroup = kLeanBlock >> lg;
-  double acc = 0.0;
-  for (int base = 0; base < nrows; base += ngroup) {   // one trip except for tiles of 1-2 entry rows
-    const int r = base + gid;
-    T sum = 0;
-    if (r < nrows) {
-      const int e = srp[r + 1];
-      for (int k = srp[r] + lig; k < e; k += g) sum += sm[k];
+  if (!s_last) return false;
+  __threadfence();
+#pragma unroll
+  for (int i = 0; i < NSLOT; i++) {
+    const bool is_max = LAST_IS_MAX && (i == NSLOT - 1);
+    double acc = 0.0;
+    for (int j = threadIdx.x; j < (int)gridDim.x; j += blockDim.x) {
+      const double v = __ldcg(red + slots[i] * stride + j);
+      acc = is_max ? fmax(acc, v) : acc + v;
     }
-    for (int o = g >> 1; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
-    if (r < nrows && lig == 0) {
-      const int row = d.x + r;
-      if (MODE == 0) {
-        out0[row] = sum;
-        out1[row] = (rho_vec ? rho_vec[row] : rho) * sum;
-      } else {
-        out0[row] = sum;
-        acc += (double)p[row] * (double)sum;
+    totals[i] = is_max ? block_max(acc, shr) : block_sum(acc, shr);
+  }
+  return true;
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(kLeanBlock, kLeanCtasPerSm) g_lean_pass(const PcgArgs* ap, PcgRun* run, double* red,
+                                                                          int stride) {
+  __shared__ T sm[kTile];
+  __shared__ int srp[kMaxRows + 1];
+  __shared__ double shr[48];
+  const PcgArgs& a = *ap;
+  // everything the tiles need is pulled out of the (global-memory) argument block once
+  constexpr bool kOverA = (MODE == 0 || MODE == 3 || MODE == 4);
+  const CsrView& M = (MODE == 4) ? a.At : (kOverA ? a.A : a.K2);
+  const int* __restrict__ row_ptr = M.row_ptr;
+  const int* __restrict__ col_ind = M.col_ind;
+  const T* __restrict__   val     = M.val;
+  const int4* __restrict__ desc   = M.desc;
+  const int nblocks = M.nblocks;
+  const T* __restrict__ src = (MODE == 4) ? a.t : ((MODE == 0 || MODE == 1 || MODE == 5) ? a.p : a.x);
+  const T* __restrict__ t = a.t;
+  const int n = a.n;
+  const int tid = threadIdx.x;
+  double acc = 0.0, acc1 = 0.0, acc2 = 0.0;
+  for (int b = blockIdx.x; b < nblocks; b += gridDim.x) {
+    const int4 d = __ldg(desc + b);
+    const int nnz0 = d.z, cnt = d.w, nrows = d.y & 0xffffff, lg = d.y >> 24;
+    for (int i = tid; i <= nrows; i += kLeanBlock) srp[i] = ld_stream(row_ptr + d.x + i) - nnz0;
+    int c[4];
+    T   v[4];
+#pragma unroll
+    for (int u = 0; u < 4; u++) {
+      const int k = u * kLeanBlock + tid;
+      if (k < cnt) {
+        c[u] = ld_stream(col_ind + nnz0 + k);
+        v[u] = ld_stream(val + nnz0 + k);
       }
     }
+#pragma unroll
+    for (int u = 0; u < 4; u++) {
+      const int k = u * kLeanBlock + tid;
+      if (k < cnt) {
+        if (kOverA) sm[k] = v[u] * src[c[u]];
+        else sm[k] = v[u] * (c[u] < n ? src[c[u]] : t[c[u] - n]);
+      }
+    }
+    __syncthreads();
+    const int g = 1 << lg, gid = tid >> lg, lig = tid & (g - 1), ngroup = kLeanBlock >> lg;
+    for (int base = 0; base < nrows; base += ngroup) {   // one trip except for tiles of 1-2 entry rows
+      const int r = base + gid;
+      T sum = 0;
+      if (r < nrows) {
+        const int e = srp[r + 1];
+        for (int k = srp[r] + lig; k < e; k += g) sum += sm[k];
+      }
+      for (int o = g >> 1; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+      if (r < nrows && lig == 0) {
+        const int row = d.x + r;
+        if (MODE == 0) {
+          a.w[row] = sum;
+          a.t[row] = (a.rho_vec ? a.rho_vec[row] : a.rho) * sum;
+        } else if (MODE == 3) {
+          a.Ax[row] = sum;
+          a.t[row]  = (a.rho_vec ? a.rho_vec[row] : a.rho) * (sum - a.b[n + row]);
+        } else if (MODE >= 4) {
+          a.Kp[row] = sum;
+        } else if (MODE == 1) {
+          // Kp and the three dots that fix alpha AND beta before the vector update:
+          //   r+ = r + alpha Kp  =>  r+' M^-1 r+ = r'y + 2 alpha r'M^-1 Kp + alpha^2 Kp'M^-1 Kp
+          a.Kp[row] = sum;
+          const T yk = a.minv[row] * sum;
+          acc  += (double)src[row] * (double)sum;
+          acc1 += (double)a.r[row] * (double)yk;
+          acc2 += (double)sum * (double)yk;
+        } else {
+          const T rr = sum - a.b[row];
+          const T yy = a.minv[row] * rr;
+          a.r[row] = rr;
+          a.p[row] = -yy;
+          acc  += (double)rr * (double)yy;
+          acc1 = fmax(acc1, fabs((double)rr));
+        }
+      }
+    }
+    __syncthreads();   // sm / srp are reused by the next tile
   }
   if (MODE == 1) {
-    acc = block_sum(acc, shr);
-    double tot;
-    if (publish<false>(acc, red, stride, SLOT_PKP, &run->ticket[SLOT_PKP], true, shr, tot) &&
-        threadIdx.x == 0) {
-      run->pKp = tot;
+    block_sum3(acc, acc1, acc2, shr);
+    const double part[3] = {acc, acc1, acc2};
+    const int slots[3] = {SLOT_PKP, SLOT_RKP, SLOT_KPKP};
+    double tot[3];
+    if (publish_fold<3, false>(part, slots, red, stride, &run->ticket[SLOT_PKP], shr, tot) && tid == 0) {
+      run->pKp = tot[0];
+      cg_step_scalars(run, tot[0], tot[1], tot[2]);
       run->ticket[SLOT_PKP] = 0;
     }
+  } else if (MODE == 2) {
+    block_sum_max(acc, acc1, shr);
+    const double part[2] = {acc, acc1};
+    const int slots[2] = {SLOT_RTY, SLOT_RMAX};
+    double tot[2];
+    if (publish_fold<2, true>(part, slots, red, stride, &run->ticket[SLOT_RTY], shr, tot) && tid == 0) {
+      run->rTy = tot[0];
+      run->rnorm = tot[1];
+      run->ticket[SLOT_RTY] = 0;
+    }
   }
+}
+
+inline int lean_grid(const b200_csr& M) {
+  const int wave = ctx().sm_count * kLeanCtasPerSm;
+  const int g = M.nblocks < wave ? M.nblocks : wave;
+  return g > 0 ? g : 1;
 }
 
 // the flat kernel does not handle chunks of over-long rows
@@ -435,6 +556,46 @@ __global__ void __launch_bounds__(kBlock) g_direction(const PcgArgs* ap, const P
     a.p[i] = beta * a.p[i] - a.minv[i] * a.r[i];
 }
 
+// L3+L4 in one kernel (graph driver): x += a p ; r += a Kp ; p = beta p - M^-1 r ; Ax += a w ;
+// totals r'y (exact), ||r||_inf ; last CTA: it++, loop condition.  8 n F + 3 m F bytes.
+__global__ void __launch_bounds__(kBlock) g_update_fused(const PcgArgs* ap, PcgRun* run, double* red, int stride,
+                                                         cudaGraphConditionalHandle h) {
+  __shared__ double shr[33];
+  const PcgArgs& a = *ap;
+  const int n = a.n, m = a.m;
+  const T alpha = (T)run->alpha, beta = (T)run->beta;
+  T* __restrict__ x = a.x; T* __restrict__ p = a.p; T* __restrict__ r = a.r;
+  const T* __restrict__ Kp = a.Kp; const T* __restrict__ minv = a.minv;
+  const int gtid = blockIdx.x * blockDim.x + threadIdx.x, gstride = gridDim.x * blockDim.x;
+  double acc_rty = 0.0, acc_max = 0.0;
+  for (int i = gtid; i < n; i += gstride) {
+    const T pi = p[i];
+    x[i] += alpha * pi;
+    const T rr = r[i] + alpha * Kp[i];
+    r[i] = rr;
+    const T yy = minv[i] * rr;
+    p[i] = beta * pi - yy;
+    acc_rty += (double)rr * (double)yy;
+    acc_max = fmax(acc_max, fabs((double)rr));
+  }
+  T* __restrict__ Ax = a.Ax; const T* __restrict__ w = a.w;
+  for (int j = gtid; j < m; j += gstride) Ax[j] += alpha * w[j];
+  acc_rty = block_sum(acc_rty, shr);
+  acc_max = block_max(acc_max, shr);
+  double tot;
+  publish<true>(acc_max, red, stride, SLOT_RMAX, nullptr, false, shr, tot);
+  if (publish<false>(acc_rty, red, stride, SLOT_RTY, &run->ticket[SLOT_RTY], true, shr, tot)) {
+    const double rmax = fold<true>(red, stride, SLOT_RMAX, shr);
+    if (threadIdx.x == 0) {
+      run->rTy   = tot;
+      run->rnorm = rmax;
+      run->it   += 1;
+      run->ticket[SLOT_RTY] = 0;
+      if (h) cudaGraphSetConditional(h, (rmax > run->eps && run->it < a.max_iter) ? 1u : 0u);
+    }
+  }
+}
+
 // E1: b1 = x ; b2 = A x (carried) or (A x - b2)/delta when polishing ; persist the schedule state
 __global__ void __launch_bounds__(kBlock) g_epilogue(const PcgArgs* ap, PcgRun* run) {
   const PcgArgs& a = *ap;
@@ -458,7 +619,10 @@ __global__ void __launch_bounds__(kBlock) g_epilogue(const PcgArgs* ap, PcgRun* 
   }
 }
 
+// one wave of co-resident CTAs looping over the tiles (see the note on per-CTA tails above)
 inline int pass_grid(const b200_csr& M, int cap) {
+  const int wave = ctx().sm_count * B200_SPMV_MINBLOCKS;
+  if (cap > wave) cap = wave;
   int g = M.nblocks < cap ? M.nblocks : cap;
   return g > 0 ? g : 1;
 }
@@ -518,7 +682,7 @@ int b200_pcg_graph_build(b200_pcg* s) {
   if (!ok) return 1;
   cudaGraph_t body = cp.conditional.phGraph_out[0];
 
-  // body: L1 -> L2 -> L3 -> L4
+  // body: L1 -> L2 -> L3+L4
   cudaGraphNode_t prev = nullptr;
   auto add = [&](void* func, dim3 grid, dim3 block, size_t smem, void** args) {
     cudaKernelNodeParams kp;
@@ -551,7 +715,7 @@ int b200_pcg_graph_build(b200_pcg* s) {
   if (s->m > 0) {
     if (lean) {
       void* a1[] = {(void*)&d_args, (void*)&d_run, (void*)&d_red, (void*)&stride};
-      add((void*)g_lean_pass<0>, dim3(s->A->nblocks), dim3(kLeanBlock), 0, a1);
+      add((void*)g_lean_pass<0>, dim3(lean_grid(*s->A)), dim3(kLeanBlock), 0, a1);
     } else {
       void* a1[] = {(void*)&d_args};
       add((void*)g_pass_A<1>, dim3(pass_grid(*s->A, cap)), dim3(kSpmvBlock), kSpmvSmemBytes, a1);
@@ -559,17 +723,15 @@ int b200_pcg_graph_build(b200_pcg* s) {
   }
   {
     void* a2[] = {(void*)&d_args, (void*)&d_run, (void*)&d_red, (void*)&stride};
-    if (lean) add((void*)g_lean_pass<1>, dim3(s->K2.nblocks), dim3(kLeanBlock), 0, a2);
+    if (lean) add((void*)g_lean_pass<1>, dim3(lean_grid(s->K2)), dim3(kLeanBlock), 0, a2);
     else add((void*)g_pass_K<1>, dim3(pass_grid(s->K2, cap)), dim3(kSpmvBlock), kSpmvSmemBytes, a2);
   }
   {
+    // L3 + L4 in one kernel: alpha AND beta are known after the fused-operator pass
     void* a3[] = {(void*)&d_args, (void*)&d_run, (void*)&d_red, (void*)&stride, (void*)&h};
     int nm = s->n > s->m ? s->n : s->m;
-    add((void*)g_update, dim3(ew_grid(nm)), dim3(kBlock), 0, a3);
-  }
-  {
-    void* a4[] = {(void*)&d_args, (void*)&d_run};
-    add((void*)g_direction, dim3(ew_grid(s->n)), dim3(kBlock), 0, a4);
+    int gu = ew_grid(nm) < cap ? ew_grid(nm) : cap;
+    add((void*)g_update_fused, dim3(gu), dim3(kBlock), 0, a3);
   }
   if (!ok) return 1;
   cudaGraphExec_t exec = nullptr;
@@ -595,31 +757,33 @@ int b200_pcg_graph_solve(b200_pcg* s, const PcgArgs& a) {
   const int cap = s->gred_stride;
   const int n = s->n, m = s->m;
   g_set_args<<<1, 32, 0, st>>>(s->d_args, a);
-  count_launch();
+  count_launch("g_set_args");
   const PcgArgs* d_args = s->d_args;
   if (a.polishing || a.admm_iter == 1) {
     if (m > 0) {
       g_rhs_t<<<ew_grid(m), kBlock, 0, st>>>(d_args);
-      count_launch();
+      count_launch("g_rhs_t");
     }
     const int g = m > 0 ? pass_grid(*s->At, cap) : (ew_grid(n) < cap ? ew_grid(n) : cap);
     g_rhs_norm<<<g, kSpmvBlock, kSpmvSmemBytes, st>>>(d_args, s->d_run, s->d_gred, cap);
-    count_launch();
+    count_launch("g_rhs_norm");
   }
   g_tolerance<<<1, 32, 0, st>>>(d_args, s->d_run);
-  count_launch();
+  count_launch("g_tolerance");
   if (m > 0) {
     if (a.ax_valid) g_p1_carried<<<ew_grid(m), kBlock, 0, st>>>(d_args);
+    else if (s->lean) g_lean_pass<3><<<lean_grid(*s->A), kLeanBlock, 0, st>>>(d_args, s->d_run, s->d_gred, cap);
     else g_pass_A<0><<<pass_grid(*s->A, cap), kSpmvBlock, kSpmvSmemBytes, st>>>(d_args);
-    count_launch();
+    count_launch("g_lean_pass<3>");
   }
-  g_pass_K<0><<<pass_grid(s->K2, cap), kSpmvBlock, kSpmvSmemBytes, st>>>(d_args, s->d_run, s->d_gred, cap);
-  count_launch();
+  if (s->lean) g_lean_pass<2><<<lean_grid(s->K2), kLeanBlock, 0, st>>>(d_args, s->d_run, s->d_gred, cap);
+  else g_pass_K<0><<<pass_grid(s->K2, cap), kSpmvBlock, kSpmvSmemBytes, st>>>(d_args, s->d_run, s->d_gred, cap);
+  count_launch("g_lean_pass<2>");
   bool ok = B200_CHECK(cudaGraphLaunch((cudaGraphExec_t)s->graph_exec, st));
-  count_launch();
+  count_launch("graph(loop)");
   const int nm = n > m ? n : m;
   g_epilogue<<<ew_grid(nm), kBlock, 0, st>>>(d_args, s->d_run);
-  count_launch();
+  count_launch("g_epilogue");
   return ok ? 0 : 1;
 }
 
@@ -693,4 +857,64 @@ int b200_pcg_sharded_solve(b200_pcg* s, const PcgArgs& a) {
   g_epilogue<<<ew_grid(nm), kBlock, 0, st>>>(d_args, run);
   count_launch();
   return ok ? 0 : 1;
+}
+
+// ------------------------------------------------------------------ phase profile (development aid)
+// Times the kernels of one CG iteration of the most recently created solver one by one (plain
+// launches, CUDA events on the library stream).  The iterate is left in an arbitrary state:
+// call it on a solver that is thrown away afterwards.
+namespace {
+b200_pcg* g_profile_target = nullptr;
+__global__ void g_nop() {}
+}
+void b200_pcg_profile_register(b200_pcg* s, bool alive) {
+  if (alive) g_profile_target = s;
+  else if (g_profile_target == s) g_profile_target = nullptr;
+}
+
+extern "C" int b200_pcg_profile_last(int reps, double* out_us, int nout) {
+  b200_pcg* s = g_profile_target;
+  if (!s || !s->d_args || !s->lean || s->sharded || nout < 12) return -1;
+  Context& c = ctx();
+  cudaStream_t st = c.stream;
+  const int cap = s->gred_stride;
+  const PcgArgs* d_args = s->d_args;
+  PcgRun* run = s->d_run;
+  double* red = s->d_gred;
+  const int n = s->n, m = s->m, nm = n > m ? n : m;
+  const int gu = ew_grid(nm) < cap ? ew_grid(nm) : cap;
+  cudaGraphConditionalHandle none = 0;
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0); cudaEventCreate(&e1);
+  auto timeit = [&](auto&& body) {
+    body();
+    cudaEventRecord(e0, st);
+    for (int i = 0; i < reps; i++) body();
+    cudaEventRecord(e1, st);
+    cudaEventSynchronize(e1);
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, e0, e1);
+    return (double)ms * 1e3 / reps;
+  };
+  auto passA  = [&] { if (m > 0) g_lean_pass<0><<<lean_grid(*s->A), kLeanBlock, 0, st>>>(d_args, run, red, cap); };
+  auto passK  = [&] { g_lean_pass<1><<<lean_grid(s->K2), kLeanBlock, 0, st>>>(d_args, run, red, cap); };
+  auto upd    = [&] { g_update_fused<<<gu, kBlock, 0, st>>>(d_args, run, red, cap, none); };
+  out_us[0]  = timeit(passA);
+  out_us[1]  = timeit(passK);
+  out_us[2]  = timeit(upd);
+  out_us[3]  = timeit([&] { passA(); passK(); upd(); });
+  out_us[4]  = timeit([&] { g_pass_K<0><<<pass_grid(s->K2, cap), kSpmvBlock, kSpmvSmemBytes, st>>>(d_args, run, red, cap); });
+  out_us[5]  = timeit([&] { g_lean_pass<2><<<lean_grid(s->K2), kLeanBlock, 0, st>>>(d_args, run, red, cap); });
+  out_us[6]  = timeit([&] { if (m > 0) g_p1_carried<<<ew_grid(m), kBlock, 0, st>>>(d_args); });
+  out_us[7]  = timeit([&] { g_epilogue<<<ew_grid(nm), kBlock, 0, st>>>(d_args, run); });
+  out_us[8]  = timeit([&] { g_update<<<gu, kBlock, 0, st>>>(d_args, run, red, cap, none); });
+  out_us[9]  = timeit([&] { g_direction<<<ew_grid(n), kBlock, 0, st>>>(d_args, run); });
+  out_us[10] = timeit([&] { g_nop<<<1, 32, 0, st>>>(); });   // launch floor
+  out_us[11] = timeit([&] { if (m > 0) g_lean_pass<3><<<lean_grid(*s->A), kLeanBlock, 0, st>>>(d_args, run, red, cap); });
+  if (nout >= 14) {
+    out_us[12] = timeit([&] { if (m > 0) g_lean_pass<4><<<lean_grid(*s->At), kLeanBlock, 0, st>>>(d_args, run, red, cap); });
+    out_us[13] = timeit([&] { g_lean_pass<5><<<lean_grid(s->K2), kLeanBlock, 0, st>>>(d_args, run, red, cap); });
+  }
+  cudaEventDestroy(e0); cudaEventDestroy(e1);
+  return 0;
 }

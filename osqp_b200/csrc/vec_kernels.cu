@@ -40,7 +40,8 @@ enum RedOp { RED_SUM = 0, RED_MAX = 1 };
 // the last CTA to arrive (ticket) folds the partials in index order and writes the scalar.
 template <int OP, class F>
 __global__ void __launch_bounds__(kBlock) reduce_kernel(int n, F f, double* partials,
-                                                        unsigned* ticket, double* out) {
+                                                        unsigned* ticket, double* out, double* mail,
+                                                        unsigned long long seq) {
   __shared__ double sh[33];
   __shared__ bool   is_last;
   const int stride = gridDim.x * blockDim.x;
@@ -70,6 +71,7 @@ __global__ void __launch_bounds__(kBlock) reduce_kernel(int n, F f, double* part
     if (threadIdx.x == 0) {
       *out    = a;
       *ticket = 0;
+      if (mail) mail_post(mail, &a, 1, seq);
     }
   }
 }
@@ -80,9 +82,17 @@ inline double run_reduce(int n, F f) {
   Context& c = ctx();
   int grid = ew_grid(n);
   if (grid > kMaxRedBlocks) grid = kMaxRedBlocks;
-  reduce_kernel<OP><<<grid, kBlock, 0, c.stream>>>(n, f, c.d_partials, c.d_ticket, c.d_scalar);
+  if (!dist_scope()) {
+    // result comes back through the mapped mailbox: no copy, no stream synchronisation
+    const unsigned long long seq = ++c.mail_seq;
+    reduce_kernel<OP><<<grid, kBlock, 0, c.stream>>>(n, f, c.d_partials, c.d_ticket, c.d_scalar, c.d_mail, seq);
+    count_launch();
+    if (mail_wait(seq)) return c.h_mail[0];
+    return 0.0;
+  }
+  reduce_kernel<OP><<<grid, kBlock, 0, c.stream>>>(n, f, c.d_partials, c.d_ticket, c.d_scalar, nullptr, 0ull);
   count_launch();
-  if (dist_scope()) dist_allreduce_f64(c.d_scalar, 1, OP == RED_MAX);   // row-sharded operand
+  dist_allreduce_f64(c.d_scalar, 1, OP == RED_MAX);   // row-sharded operand
   B200_CHECK(cudaMemcpyAsync(c.h_scalar, c.d_scalar, sizeof(double), cudaMemcpyDeviceToHost, c.stream));
   B200_CHECK(cudaStreamSynchronize(c.stream));
   return c.h_scalar[0];
@@ -288,8 +298,8 @@ __device__ __forceinline__ bool res_is_sum(int s) {
 }
 
 __global__ void __launch_bounds__(kBlock) residuals_kernel(ResArgs a, double* partials, unsigned* ticket,
-                                                           double* out) {
-  __shared__ double sh[33];
+                                                           double* out, double* mail, unsigned long long seq) {
+  __shared__ double shw[B200_RES_COUNT][kBlock / 32];
   __shared__ bool is_last;
   double v[B200_RES_COUNT];
 #pragma unroll
@@ -334,29 +344,49 @@ __global__ void __launch_bounds__(kBlock) residuals_kernel(ResArgs a, double* pa
     v[B200_RES_XPX] += Px * x;
     v[B200_RES_QX]  += q * x;
   }
+  // CTA partials with ONE barrier: warp shuffles, per-warp results in shared memory, then thread s
+  // folds slot s over the warps
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
 #pragma unroll
   for (int s = 0; s < B200_RES_COUNT; s++) {
-    const double r = res_is_sum(s) ? block_sum(v[s], sh) : block_max(v[s], sh);
-    if (threadIdx.x == 0) partials[s * gridDim.x + blockIdx.x] = r;
+    const double r = res_is_sum(s) ? warp_sum(v[s]) : warp_max(v[s]);
+    if (lane == 0) shw[s][w] = r;
   }
-  if (threadIdx.x == 0) {
+  __syncthreads();
+  if (threadIdx.x < B200_RES_COUNT) {
+    const int s = threadIdx.x;
+    double acc = 0.0;
+    for (int k = 0; k < kBlock / 32; k++) acc = res_is_sum(s) ? acc + shw[s][k] : fmax(acc, shw[s][k]);
+    partials[s * gridDim.x + blockIdx.x] = acc;
     __threadfence();
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
     const unsigned t = atomicAdd(ticket, 1u);
     is_last = (t == gridDim.x - 1);
   }
   __syncthreads();
   if (is_last) {
     __threadfence();
-    for (int s = 0; s < B200_RES_COUNT; s++) {
+    // warp w folds slots w, w + 8, ... in index order; no CTA barriers
+    for (int s = w; s < B200_RES_COUNT; s += kBlock / 32) {
       double acc = 0.0;
-      for (int b = threadIdx.x; b < gridDim.x; b += blockDim.x) {
+      for (int b = lane; b < gridDim.x; b += 32) {
         const double p = __ldcg(&partials[s * gridDim.x + b]);
         acc = res_is_sum(s) ? acc + p : fmax(acc, p);
       }
-      acc = res_is_sum(s) ? block_sum(acc, sh) : block_max(acc, sh);
-      if (threadIdx.x == 0) out[s] = acc;
+      acc = res_is_sum(s) ? warp_sum(acc) : warp_max(acc);
+      if (lane == 0) { out[s] = acc; shw[s][0] = acc; }
     }
-    if (threadIdx.x == 0) *ticket = 0;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      *ticket = 0;
+      if (mail) {
+        double vals[B200_RES_COUNT];
+        for (int s = 0; s < B200_RES_COUNT; s++) vals[s] = shw[s][0];
+        mail_post(mail, vals, B200_RES_COUNT, seq);
+      }
+    }
   }
 }
 
@@ -370,7 +400,16 @@ extern "C" void b200_admm_residuals(const T* x, const T* y, const T* z, const T*
   const int nm = n > m ? n : m;
   int grid = ew_grid(nm);
   if (grid > kMaxRedBlocks) grid = kMaxRedBlocks;
-  residuals_kernel<<<grid, kBlock, 0, c.stream>>>(a, c.d_partials, c.d_ticket, c.d_scalar);
+  if (!dist_active()) {
+    const unsigned long long seq = ++c.mail_seq;
+    residuals_kernel<<<grid, kBlock, 0, c.stream>>>(a, c.d_partials, c.d_ticket, c.d_scalar, c.d_mail, seq);
+    count_launch();
+    if (mail_wait(seq)) {
+      for (int s = 0; s < B200_RES_COUNT; s++) h_out[s] = c.h_mail[s];
+      return;
+    }
+  }
+  residuals_kernel<<<grid, kBlock, 0, c.stream>>>(a, c.d_partials, c.d_ticket, c.d_scalar, nullptr, 0ull);
   count_launch();
   if (dist_active()) {
     // slots 0..5 are maxima over the row-sharded m-vectors, slot 6 (support function) a sum over

@@ -56,6 +56,112 @@ def shard_problem(pb, rank, world):
                 u=np.asarray(pb["u"])[r0:r1], rows=(r0, r1), bounds=bounds)
 
 
+# --------------------------------------------------------------------------------------------
+# Shared / local column split (SURVEY.md section 8e "recommended refinement")
+#
+# With plain row blocks every n-vector is replicated, so the BLAS-1 work and the all-reduce volume
+# do not shrink with the number of ranks -- fatal for epigraph-style problems (Huber, SVM, Lasso)
+# whose slack variables outnumber the features 1000:1.  Here rows that are linked through
+# low-degree columns (a slack variable and the 2-3 rows it appears in) are first clustered with a
+# union-find so that they land on the same rank; a column is then LOCAL to a rank if all its
+# nonzeros (and its couplings in P) live there, and SHARED otherwise.  Each rank solves over
+# [shared columns ; its local columns]: only the shared slice is ever exchanged.
+
+def plan_column_split(P, A, world, max_link_degree=3):
+    """Returns a dict with, per rank r: rows[r] (global row ids), cols[r] = shared ++ local_r (global
+    column ids), and `shared` (global ids of the shared columns, identical leading part of cols[r])."""
+    A = sp.csc_matrix(A)
+    m, n = A.shape
+    Ptri = sp.triu(sp.csc_matrix(P), k=1).tocoo()
+    deg = np.diff(A.indptr)
+    # 1. cluster rows through low-degree columns (connected components of the row graph whose
+    #    edges join the first row of every linking column to its other rows)
+    from scipy.sparse.csgraph import connected_components
+    link = np.nonzero((deg >= 2) & (deg <= max_link_degree))[0]
+    if link.size:
+        starts = A.indptr[link]
+        src, dst = [], []
+        for t in range(1, max_link_degree):
+            has = deg[link] > t
+            src.append(A.indices[starts[has]])
+            dst.append(A.indices[starts[has] + t])
+        src, dst = np.concatenate(src), np.concatenate(dst)
+        G = sp.coo_matrix((np.ones(src.size, dtype=np.int8), (src, dst)), shape=(m, m))
+        _, comp = connected_components(G, directed=False)
+    else:
+        comp = np.arange(m)
+    # label every cluster by its first row so that clusters keep the original row order
+    first = np.full(comp.max() + 1, m, dtype=np.int64)
+    np.minimum.at(first, comp, np.arange(m))
+    root = first[comp]
+    # 2. clusters -> ranks, greedy in order of first row, balanced by nonzeros (+1 per row)
+    Acsr = A.tocsr()
+    w_row = np.diff(Acsr.indptr).astype(np.int64) + 1
+    order = np.argsort(root, kind="stable")                 # rows grouped by cluster, clusters by first row
+    w_sorted = w_row[order]
+    cum = np.cumsum(w_sorted)
+    target = cum[-1] / world
+    rank_sorted = np.minimum((cum - w_sorted) // max(target, 1), world - 1).astype(np.int64)
+    # a cluster must not straddle two ranks: every row takes the rank of its cluster's first row
+    first_of_cluster = np.concatenate([[True], root[order][1:] != root[order][:-1]])
+    start_idx = np.maximum.accumulate(np.where(first_of_cluster, np.arange(len(order)), 0))
+    cl_rank = rank_sorted[start_idx]
+    rank_of_row = np.empty(m, dtype=np.int64)
+    rank_of_row[order] = cl_rank
+    # 3. classify columns
+    owner = np.full(n, -1, dtype=np.int64)
+    col_of_entry = np.repeat(np.arange(n), deg)
+    r_entry = rank_of_row[A.indices]
+    lo = np.full(n, world, dtype=np.int64)
+    hi = np.full(n, -1, dtype=np.int64)
+    np.minimum.at(lo, col_of_entry, r_entry)
+    np.maximum.at(hi, col_of_entry, r_entry)
+    single = (deg > 0) & (lo == hi)
+    owner[single] = lo[single]
+    # columns coupled through P must live together: shared wins, propagate until stable
+    if Ptri.nnz:
+        changed = True
+        while changed:
+            bad = owner[Ptri.row] != owner[Ptri.col]
+            touch = np.unique(np.concatenate([Ptri.row[bad], Ptri.col[bad]]))
+            touch = touch[owner[touch] >= 0]
+            changed = touch.size > 0
+            owner[touch] = -1
+    shared = np.nonzero(owner < 0)[0]
+    # quality guard: if the cut is lopsided (an empty or 2x overloaded rank) or barely anything is
+    # local, fall back to plain contiguous row blocks with every column shared
+    cnt = np.bincount(rank_of_row, weights=w_row, minlength=world)
+    if cnt.min() == 0 or cnt.max() > 2.0 * cnt.mean() or shared.size > 0.5 * n:
+        bounds = partition_rows(Acsr, world, n=-1)
+        rank_of_row = np.repeat(np.arange(world), np.diff(bounds))
+        owner[:] = -1
+        shared = np.arange(n)
+    rows, cols = [], []
+    for r in range(world):
+        rows.append(np.nonzero(rank_of_row == r)[0])
+        cols.append(np.concatenate([shared, np.nonzero(owner == r)[0]]))
+    return dict(shared=shared, rows=rows, cols=cols, n=n, m=m, world=world)
+
+
+def shard_problem_split(pb, rank, plan):
+    """Rank `rank`'s QP under a column-split plan.  A row with no entries and infinite bounds is
+    appended when the local problem would otherwise have as many rows as columns (the backend
+    tells row vectors from column vectors by their length)."""
+    A = sp.csr_matrix(pb["A"])
+    P = sp.csc_matrix(pb["P"])
+    R, Cc = plan["rows"][rank], plan["cols"][rank]
+    A_r = A[R][:, Cc].tocsc()
+    P_r = sp.triu(P[Cc][:, Cc], format="csc")
+    l, u = np.asarray(pb["l"], dtype=float)[R], np.asarray(pb["u"], dtype=float)[R]
+    padded = 0
+    if A_r.shape[0] == A_r.shape[1]:
+        A_r = sp.vstack([A_r, sp.csc_matrix((1, A_r.shape[1]))], format="csc")
+        l, u = np.append(l, -np.inf), np.append(u, np.inf)
+        padded = 1
+    return dict(P=P_r, q=np.asarray(pb["q"], dtype=float)[Cc], A=A_r, l=l, u=u, padded=padded,
+                n_shared=int(plan["shared"].size))
+
+
 def exchange_unique_id(make_id, dist):
     """rank 0 creates the NCCL unique id, everybody receives it (works on any backend)."""
     import torch
