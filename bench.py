@@ -212,6 +212,14 @@ def pcg_roofline(k, pb, kcg):
             times.append(ms)
     li = C.c_int(0)
     k.b200_pcg_stats(pcg, None, None, C.byref(li), None, None)
+    # graph driver (the default at this size): per-kernel CUDA-event times of one CG iteration
+    k.b200_pcg_profile_last.argtypes = [C.c_int, C.POINTER(C.c_double), C.c_int]
+    k.b200_pcg_profile_last.restype = C.c_int
+    ph = (C.c_double * 14)()
+    phases = None
+    if k.b200_pcg_profile_last(20, ph, 14) == 0:
+        phases = {"pass_A_us": ph[0], "pass_K2_us": ph[1], "update_us": ph[2], "iteration_us": ph[3],
+                  "initial_residual_pass_us": ph[5]}
     k.b200_pcg_destroy(pcg)
     for h in (hP, hA, hAt):
         k.b200_csr_destroy(h)
@@ -226,8 +234,21 @@ def pcg_roofline(k, pb, kcg):
     fixed = spmv(n, n + m, nnzK) + (3 * n + 3 * m) * F
     byts = fixed + li.value * per_iter
     ms = float(np.mean(times))
-    return {"kernel": "pcg_kernel", "cg_iters_per_launch": li.value, "bytes_per_launch": byts,
-            "bytes_per_cg_iter": per_iter, "ms_per_launch": ms, "gbs": byts / ms / 1e6}
+    out = {"kernel": "pcg_kernel", "cg_iters_per_launch": li.value, "bytes_per_launch": byts,
+           "bytes_per_cg_iter": per_iter, "ms_per_launch": ms, "gbs": byts / ms / 1e6}
+    if phases is not None:
+        # the dominant kernel of the graph driver is the fused-operator pass (one launch per CG
+        # iteration + one per solve): its own algorithmic bytes = SpMV([P+sigma I | A']) + the
+        # p, r, M^-1 reads of the three fused dot products
+        kb = spmv(n, n + m, nnzK) + 3 * n * F
+        out.update({"kernel": "g_lean_pass<1> (fused-operator pass Kp = [P+sigma I | A'][p; t] + 3 dots)",
+                    "bytes_per_launch": kb, "ms_per_launch": phases["pass_K2_us"] / 1e3,
+                    "gbs": kb / phases["pass_K2_us"] / 1e3,
+                    "solve": {"cg_iters": li.value, "bytes": byts, "ms": ms, "gbs": byts / ms / 1e6},
+                    "pass_A": {"bytes": spmv(m, n, nnzA), "us": phases["pass_A_us"],
+                               "gbs": spmv(m, n, nnzA) / phases["pass_A_us"] / 1e3},
+                    "phases_us": phases})
+    return out
 
 
 def run_b200(args):
@@ -340,8 +361,10 @@ def run_b200(args):
         if tp.exists() and roof is not None:
             try:
                 tj = json.loads(tp.read_text())
-                # only comparable when the ncu capture ran the same number of CG iterations per launch
-                if tj.get("cg_iters_per_launch") == roof["cg_iters_per_launch"]:
+                # only comparable for the same kernel (and, for the persistent kernel, the same
+                # number of CG iterations per launch)
+                if roof["kernel"].startswith(tj.get("kernel", "?")) and (
+                        tj.get("cg_iters_per_launch") in (None, roof["cg_iters_per_launch"])):
                     traffic = tj.get("dram_bytes_per_launch")
             except (ValueError, OSError):
                 traffic = None
@@ -369,7 +392,7 @@ def run_b200(args):
             "config": {"workload": ("lasso_1e5x1e6 (BASELINE configs[1])" if (args.scale == 1.0 and args.workload == "lasso")
                                     else f"{args.workload} generator at scale {args.scale}"),
                        "n": n, "m": m, "nnzA": nnzA, "nnzP": nnzP, "eps": 1e-3,
-                       "solver": "indirect: persistent-kernel Jacobi PCG on the reduced KKT system",
+                       "solver": "indirect: device-resident Jacobi PCG on the reduced KKT system (CUDA-graph WHILE loop of lean sm_100a passes)",
                        "step": "one cold-start osqp_solve to eps 1e-3",
                        "parallelism": ("1 GPU" if world == 1 else
                                        (f"one QP row-sharded over {world} GPUs, 1 NCCL all-reduce (n doubles) per K.p"
@@ -393,6 +416,9 @@ def run_b200(args):
                                "kernel": roof["kernel"], "cg_iters_per_launch": roof["cg_iters_per_launch"],
                                "bytes_per_launch": roof["bytes_per_launch"],
                                "ms_per_launch": roof["ms_per_launch"]}
+            for extra in ("solve", "pass_A", "phases_us"):
+                if extra in roof:
+                    out["roofline"][extra] = roof[extra]
         out["cpu_baseline"] = cpu
         args.emit(json.dumps(out))
     if dist is not None:

@@ -321,12 +321,15 @@ b200_pcg* b200_pcg_create(const b200_csr* P, const b200_csr* A, const b200_csr* 
   s->grid = (int)(want < s->max_grid ? want : s->max_grid);
   ok &= B200_CHECK(dev_malloc(&s->d_red, sizeof(double) * SLOT_COUNT * s->max_grid));
   if (!ok) { b200_pcg_destroy(s); return nullptr; }
-  // driver choice: the graph driver (lean kernels, WHILE node) pays ~8 launches per solve
-  // (measured round 1: the two drivers are within 5 % of each other on the 1.14e7-nnz Lasso, so the
-  // persistent kernel stays the default; B200_PCG_DRIVER=graph selects the graph driver, which is
-  // also the structure a row-sharded solve needs: kernel boundaries where the all-reduce goes)
+  // driver choice: the graph driver (lean one-wave / one-CTA-per-tile kernels, WHILE node) costs ~6
+  // launches per solve but runs its passes at full occupancy: measured on the 1.14e7-nnz Lasso
+  // 113 ms against 121 ms per ADMM solve for the persistent kernel (profiles/r01_phase_profile.md),
+  // so it is the default from kGraphDriverMinNnz stored entries; B200_PCG_DRIVER=graph|persistent
+  // overrides.  It is also the structure a row-sharded solve needs: kernel boundaries where the
+  // all-reduce goes.
   const char* env = getenv("B200_PCG_DRIVER");
-  s->use_graph = env ? (strcmp(env, "graph") == 0) : 0;
+  const long long work = (long long)K.nnz + (A ? (long long)A->nnz : 0);
+  s->use_graph = env ? (strcmp(env, "graph") == 0) : (work >= kGraphDriverMinNnz);
   if (dist_active()) {
     s->sharded   = 1;
     s->use_graph = 1;                       // shares the lean kernels and device structs

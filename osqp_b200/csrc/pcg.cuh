@@ -13,6 +13,9 @@ namespace b200 {
 constexpr double kCgTolMin    = 1e-7;   // OSQP_CG_TOL_MIN    (osqp_api_constants.h:215)
 constexpr double kCgPolishTol = 1e-5;   // OSQP_CG_POLISH_TOL (osqp_api_constants.h:216)
 constexpr int    kAxResync    = 50;     // solves between exact recomputations of the carried A x
+// stored entries (A + fused operator) from which the graph driver is the default: below, the
+// ~8 launches of a graph solve cost more than the persistent kernel's lower occupancy
+constexpr long long kGraphDriverMinNnz = 2000000;
 
 enum { SLOT_RHS = 0, SLOT_RTY = 1, SLOT_RMAX = 2, SLOT_PKP = 3, SLOT_RKP = 4, SLOT_KPKP = 5, SLOT_COUNT = 6 };
 

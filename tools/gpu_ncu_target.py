@@ -24,5 +24,12 @@ KCG = int(sys.argv[2]) if len(sys.argv) > 2 else 3
 for rep in range(4):
     k.b200_copy_in(bvec.ptr, rhs[rep % 2].ptr, (n + m) * 8)
     k.b200_pcg_solve(pcg, bvec.ptr, 2, 0.0, 0.0, KCG, 0.15, 10)
+# the loop-body kernels of the graph driver cannot be profiled inside a conditional graph: launch
+# them as plain kernels (b200_pcg_profile_last) so that ncu sees them
+import ctypes as C
+k.b200_pcg_profile_last.argtypes = [C.c_int, C.POINTER(C.c_double), C.c_int]
+k.b200_pcg_profile_last.restype = C.c_int
+buf = (C.c_double * 14)()
+rc = k.b200_pcg_profile_last(2, buf, 14)
 k.b200_sync()
-print("done", k.b200_last_error())
+print("done", k.b200_last_error(), "profile rc", rc, [round(v, 1) for v in buf])

@@ -99,6 +99,94 @@ __global__ void __launch_bounds__(256) k_warptile(const int* __restrict__ rp, co
   }
 }
 
+
+// ---------------- variant D: persistent CTA-tile with the NEXT tile's (col, val, row_ptr) prefetched into
+// registers while the current tile is gathered and reduced (hides the HBM latency of the stream)
+template <int BLOCK, int KU, int MINB>
+__global__ void __launch_bounds__(BLOCK, MINB) k_tile_pf(const int* __restrict__ rp, const int* __restrict__ ci,
+                                                         const T* __restrict__ va, const Desc* __restrict__ desc, int nblocks,
+                                                         const T* __restrict__ x, T* __restrict__ y) {
+  constexpr int TILE = BLOCK * KU;
+  constexpr int NRP = (TILE / 2 + BLOCK) / BLOCK;      // row pointers per thread (<= TILE/2 + 1 rows)
+  __shared__ T sm[TILE];
+  __shared__ int srp[TILE / 2 + 1];
+  const int tid = threadIdx.x;
+  int b = blockIdx.x;
+  if (b >= nblocks) return;
+  Desc d = desc[b];
+  int c[KU]; T v[KU]; int rpr[NRP];
+#pragma unroll
+  for (int u = 0; u < KU; u++) { int k = u * BLOCK + tid; if (k < d.cnt) { c[u] = lds_i(ci + d.nnz0 + k); v[u] = lds_d(va + d.nnz0 + k); } }
+#pragma unroll
+  for (int u = 0; u < NRP; u++) { int i = u * BLOCK + tid; if (i <= d.nrows) rpr[u] = lds_i(rp + d.row0 + i) - d.nnz0; }
+  for (;;) {
+    // gathers of the current tile
+    T g[KU];
+#pragma unroll
+    for (int u = 0; u < KU; u++) { int k = u * BLOCK + tid; g[u] = (k < d.cnt) ? __ldg(x + c[u]) : (T)0; }
+#pragma unroll
+    for (int u = 0; u < NRP; u++) { int i = u * BLOCK + tid; if (i <= d.nrows) srp[i] = rpr[u]; }
+    // prefetch of the next tile (registers)
+    const int bn = b + gridDim.x;
+    Desc dn = d;
+    int cn[KU]; T vn[KU];
+    if (bn < nblocks) {
+      dn = desc[bn];
+#pragma unroll
+      for (int u = 0; u < KU; u++) { int k = u * BLOCK + tid; if (k < dn.cnt) { cn[u] = lds_i(ci + dn.nnz0 + k); vn[u] = lds_d(va + dn.nnz0 + k); } }
+#pragma unroll
+      for (int u = 0; u < NRP; u++) { int i = u * BLOCK + tid; if (i <= dn.nrows) rpr[u] = lds_i(rp + dn.row0 + i) - dn.nnz0; }
+    }
+#pragma unroll
+    for (int u = 0; u < KU; u++) { int k = u * BLOCK + tid; if (k < d.cnt) sm[k] = v[u] * g[u]; }
+    __syncthreads();
+    const int gg = 1 << d.lg, gid = tid >> d.lg, lig = tid & (gg - 1), ng = BLOCK >> d.lg;
+    for (int base = 0; base < d.nrows; base += ng) {
+      int r = base + gid; T acc = 0;
+      if (r < d.nrows) { int e = srp[r + 1]; for (int k = srp[r] + lig; k < e; k += gg) acc += sm[k]; }
+      for (int o = gg >> 1; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+      if (r < d.nrows && lig == 0) y[d.row0 + r] = acc;
+    }
+    __syncthreads();
+    if (bn >= nblocks) break;
+    b = bn; d = dn;
+#pragma unroll
+    for (int u = 0; u < KU; u++) { c[u] = cn[u]; v[u] = vn[u]; }
+  }
+}
+
+
+// ---------------- variant E: warp-autonomous tiles (no CTA barrier): each warp owns WT-entry tiles of whole
+// rows, stages products in its private shared-memory segment, __syncwarp, group-reduces its rows
+template <int WT, int WARPS, int MINB>
+__global__ void __launch_bounds__(WARPS * 32, MINB) k_warp(const int* __restrict__ rp, const int* __restrict__ ci,
+                                                          const T* __restrict__ va, const Desc* __restrict__ desc, int nblocks,
+                                                          const T* __restrict__ x, T* __restrict__ y) {
+  constexpr int KU = WT / 32;
+  __shared__ T sm_all[WARPS][WT];
+  __shared__ int srp_all[WARPS][WT / 2 + 1];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  T* sm = sm_all[w]; int* srp = srp_all[w];
+  for (int b = blockIdx.x * WARPS + w; b < nblocks; b += gridDim.x * WARPS) {
+    const Desc d = desc[b];
+    for (int i = lane; i <= d.nrows; i += 32) srp[i] = lds_i(rp + d.row0 + i) - d.nnz0;
+    int c[KU]; T v[KU];
+#pragma unroll
+    for (int u = 0; u < KU; u++) { int k = u * 32 + lane; if (k < d.cnt) { c[u] = lds_i(ci + d.nnz0 + k); v[u] = lds_d(va + d.nnz0 + k); } }
+#pragma unroll
+    for (int u = 0; u < KU; u++) { int k = u * 32 + lane; if (k < d.cnt) sm[k] = v[u] * __ldg(x + c[u]); }
+    __syncwarp();
+    const int g = 1 << d.lg, gid = lane >> d.lg, lig = lane & (g - 1), ng = 32 >> d.lg;
+    for (int base = 0; base < d.nrows; base += ng) {
+      int r = base + gid; T acc = 0;
+      if (r < d.nrows) { int e = srp[r + 1]; for (int k = srp[r] + lig; k < e; k += g) acc += sm[k]; }
+      for (int o = g >> 1; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+      if (r < d.nrows && lig == 0) y[d.row0 + r] = acc;
+    }
+    __syncwarp();
+  }
+}
+
 template <class F> float timeit(F f, int reps = 20) {
   cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
   for (int i = 0; i < 3; i++) f();
@@ -161,12 +249,23 @@ int main(int argc, char** argv) {
       check(nm, timeit([&] { k_tile<BLOCK, TILE, KU, 0><<<g, BLOCK>>>(drp, dci, dva, dd, nb, dx, dy); })); \
     }                                                                                                   \
   }
-  SWEEP(64, 256, 4) SWEEP(64, 512, 8) SWEEP(128, 512, 4) SWEEP(128, 1024, 8) SWEEP(256, 1024, 4)
-  SWEEP(256, 2048, 8) SWEEP(256, 1536, 6) SWEEP(512, 2048, 4) SWEEP(128, 768, 6) SWEEP(256, 768, 3)
-  {
-    auto d2 = schedule(rp, 256, 64, 32); Desc* dd2 = upload(d2); int nb2 = (int)d2.size();
-    check("warptile256 (thread/row) grid=148*8", timeit([&] { k_warptile<256><<<148 * 8, 256>>>(drp, dci, dva, dd2, nb2, dx, dy); }));
-    check("warptile256 (thread/row) grid=148*4", timeit([&] { k_warptile<256><<<148 * 4, 256>>>(drp, dci, dva, dd2, nb2, dx, dy); }));
+  SWEEP(256, 1024, 4) SWEEP(512, 2048, 4)
+#define PF(BLOCK, KU, MINB)                                                                             \
+  {                                                                                                     \
+    auto d = schedule(rp, BLOCK * KU, BLOCK * KU / 2, BLOCK); Desc* dd = upload(d); int nb = (int)d.size(); \
+    int g = std::min(nb, 148 * MINB); char nm[96];                                                      \
+    snprintf(nm, 96, "prefetch tile%d b%d ku%d grid=148x%d", BLOCK * KU, BLOCK, KU, MINB);             \
+    check(nm, timeit([&] { k_tile_pf<BLOCK, KU, MINB><<<g, BLOCK>>>(drp, dci, dva, dd, nb, dx, dy); })); \
   }
+  PF(512, 4, 3)
+#define WV(WT, WARPS, MINB, PERCTA)                                                                      \
+  {                                                                                                     \
+    auto d = schedule(rp, WT, WT / 2, 32); Desc* dd = upload(d); int nb = (int)d.size();                \
+    int g = PERCTA ? (nb + WARPS * PERCTA - 1) / (WARPS * PERCTA) : 148 * MINB; char nm[96];            \
+    snprintf(nm, 96, "warp tile%d warps%d minb%d grid=%d", WT, WARPS, MINB, g);                        \
+    check(nm, timeit([&] { k_warp<WT, WARPS, MINB><<<g, WARPS * 32>>>(drp, dci, dva, dd, nb, dx, dy); })); \
+  }
+  WV(128, 8, 8, 0) WV(128, 8, 8, 1) WV(128, 8, 8, 4) WV(256, 8, 6, 0) WV(256, 8, 6, 1) WV(256, 8, 6, 4)
+  WV(128, 4, 16, 1) WV(128, 4, 16, 4) WV(64, 8, 8, 1) WV(64, 8, 8, 8) WV(256, 4, 12, 2) WV(512, 8, 3, 1)
   return 0;
 }
