@@ -55,6 +55,16 @@ struct OSQPMatrix_ {
 extern OSQPInt b200_dist_n;
 extern OSQPInt b200_dist_mlocal;
 #define B200_IS_SHARDED(len) (b200_dist_mlocal >= 0 && (len) == b200_dist_mlocal && b200_dist_world() > 1)
+/*
+ * Column-split refinement (osqp_b200_dist_configure_split): the rank's QP is
+ * posed over [n_shared columns touched by several ranks ; the columns only this rank touches], so
+ * b200_dist_n is the LOCAL column count and every vector of that length is COLUMN-SPLIT: its leading
+ * n_shared entries are replicated on all ranks (reductions count them on rank 0 only), the rest is
+ * owned.  n_local must differ from m_local (the partitioner pads a free row if needed).
+ */
+extern OSQPInt b200_dist_nshared;   /* -1: layout off */
+extern OSQPInt b200_dist_nglobal;   /* global number of columns (mean over columns in scaling.c:123-124) */
+#define B200_IS_COLSPLIT(len) (b200_dist_nshared >= 0 && (len) == b200_dist_n && b200_dist_world() > 1)
 
 /*
  * Scalar cache: the fused termination check (fused_admm.c) computes every norm the core asks for

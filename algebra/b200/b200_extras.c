@@ -42,7 +42,22 @@ OSQPInt osqp_b200_sizeof(OSQPInt which) {
  * rows of A held by this rank (must differ from n).  m_local < 0 switches the mode off. */
 OSQPInt osqp_b200_dist_configure(OSQPInt n, OSQPInt m_local) {
   if (m_local >= 0 && m_local == n) return 1;
-  b200_dist_n      = n;
-  b200_dist_mlocal = m_local;
+  b200_dist_n       = n;
+  b200_dist_mlocal  = m_local;
+  b200_dist_nshared = -1;
+  b200_dist_nglobal = -1;
+  b200_dist_set_split(-1);
+  return 0;
+}
+
+/* Column-split layout: this rank's QP has n_local = n_shared + (owned columns) variables and m_local
+ * rows; n_global is the column count of the whole problem.  n_local must differ from m_local. */
+OSQPInt osqp_b200_dist_configure_split(OSQPInt n_local, OSQPInt m_local, OSQPInt n_shared, OSQPInt n_global) {
+  if (n_local == m_local || n_shared < 0 || n_shared > n_local) return 1;
+  b200_dist_n       = n_local;
+  b200_dist_mlocal  = m_local;
+  b200_dist_nshared = n_shared;
+  b200_dist_nglobal = n_global;
+  b200_dist_set_split((int)n_shared);
   return 0;
 }

@@ -390,14 +390,16 @@ void OSQPMatrix_Atxpy(const OSQPMatrix* A, const OSQPVectorf* x, OSQPVectorf* y,
   if (!A->is_symmetric && b200_dist_world() > 1 && b200_dist_mlocal >= 0) {
     /* row-sharded A: A'x = sum over ranks of A_r' x_r -> one all-reduce of the length-n result.
        beta y must be added once, after the exchange. */
+    /* column-split layout: only the shared leading slice has contributions from other ranks */
+    int nx = b200_dist_nshared >= 0 ? (int)b200_dist_nshared : (int)y->length;
     if (beta == 0.0) {
       b200_csr_spmv(A->St, x->d_val, y->d_val, alpha, 0.0);
-      b200_dist_allreduce_sum(y->d_val, (int)y->length);
+      b200_dist_allreduce_sum(y->d_val, nx);
     } else {
       OSQPFloat* tmp = (OSQPFloat*)b200_malloc((size_t)y->length * sizeof(OSQPFloat));
       if (!tmp) return;
       b200_csr_spmv(A->St, x->d_val, tmp, alpha, 0.0);
-      b200_dist_allreduce_sum(tmp, (int)y->length);
+      b200_dist_allreduce_sum(tmp, nx);
       b200_vec_add_scaled(y->d_val, 1.0, tmp, beta, y->d_val, (int)y->length);
       b200_free(tmp);
     }
@@ -422,7 +424,8 @@ void OSQPMatrix_col_norm_inf(const OSQPMatrix* M, OSQPVectorf* E) {
   else {
     b200_csr_row_absmax(M->St, E->d_val);
     /* row-sharded A: a column's norm is the max over the ranks' row blocks */
-    if (b200_dist_world() > 1 && b200_dist_mlocal >= 0) b200_dist_allreduce_max(E->d_val, (int)E->length);
+    if (b200_dist_world() > 1 && b200_dist_mlocal >= 0)
+      b200_dist_allreduce_max(E->d_val, b200_dist_nshared >= 0 ? (int)b200_dist_nshared : (int)E->length);
   }
 }
 

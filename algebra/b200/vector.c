@@ -236,19 +236,30 @@ void OSQPVectorf_set_scalar_if_gt(OSQPVectorf* x, const OSQPVectorf* z, OSQPFloa
 /* ------------------------------------------------------------------ reductions
  * each returns a host scalar by value and is therefore one stream synchronisation */
 
-OSQPInt b200_dist_n      = -1;
-OSQPInt b200_dist_mlocal = -1;
+OSQPInt b200_dist_n       = -1;
+OSQPInt b200_dist_mlocal  = -1;
+OSQPInt b200_dist_nshared = -1;
+OSQPInt b200_dist_nglobal = -1;
 
-/* reductions over row-sharded vectors are combined across ranks inside the kernel library */
-#define DIST_REDUCE(len, expr)                  \
-  do {                                          \
-    if (B200_IS_SHARDED(len)) {                 \
-      b200_dist_scope(1);                       \
-      expr;                                     \
-      b200_dist_scope(0);                       \
-    } else {                                    \
-      expr;                                     \
-    }                                           \
+/* Reductions over row-sharded vectors are combined across ranks inside the kernel library.  Over a
+ * column-split vector a rank other than 0 skips the replicated leading slice: `expr` must address
+ * its operands through RED_OFF / RED_CNT. */
+#define DIST_REDUCE(len, expr)                                          \
+  do {                                                                  \
+    OSQPInt RED_OFF = 0, RED_CNT = (len);                               \
+    int     split_  = B200_IS_COLSPLIT(len);                            \
+    if (split_ && b200_dist_rank() > 0) {                               \
+      RED_OFF = b200_dist_nshared;                                      \
+      RED_CNT = (len) - RED_OFF;                                        \
+    }                                                                   \
+    (void)RED_OFF; (void)RED_CNT;                                       \
+    if (B200_IS_SHARDED(len) || split_) {                               \
+      b200_dist_scope(1);                                               \
+      expr;                                                             \
+      b200_dist_scope(0);                                               \
+    } else {                                                            \
+      expr;                                                             \
+    }                                                                   \
   } while (0)
 
 static b200_norm_cache g_cache;
@@ -307,7 +318,7 @@ OSQPFloat OSQPVectorf_norm_inf(const OSQPVectorf* v) {
   OSQPFloat cached;
   int       live = b200_norm_cache_live();
   if (b200_norm_cache_get(OSQP_NULL, v->d_val, &cached)) return cached;
-  DIST_REDUCE(v->length, cached = b200_vec_norm_inf(v->d_val, v->length));
+  DIST_REDUCE(v->length, cached = b200_vec_norm_inf(v->d_val + RED_OFF, RED_CNT));
   b200_norm_cache_after(live, OSQP_NULL, 0);     /* a reduction writes no vector */
   return cached;
 }
@@ -316,20 +327,24 @@ OSQPFloat OSQPVectorf_scaled_norm_inf(const OSQPVectorf* S, const OSQPVectorf* v
   OSQPFloat cached;
   int       live = b200_norm_cache_live();
   if (b200_norm_cache_get(S->d_val, v->d_val, &cached)) return cached;
-  DIST_REDUCE(v->length, cached = b200_vec_scaled_norm_inf(S->d_val, v->d_val, v->length));
+  DIST_REDUCE(v->length, cached = b200_vec_scaled_norm_inf(S->d_val + RED_OFF, v->d_val + RED_OFF, RED_CNT));
   b200_norm_cache_after(live, OSQP_NULL, 0);
   return cached;
 }
 
 OSQPFloat OSQPVectorf_norm_inf_diff(const OSQPVectorf* a, const OSQPVectorf* b) {
   OSQPFloat r;
-  DIST_REDUCE(a->length, r = b200_vec_norm_inf_diff(a->d_val, b->d_val, a->length));
+  DIST_REDUCE(a->length, r = b200_vec_norm_inf_diff(a->d_val + RED_OFF, b->d_val + RED_OFF, RED_CNT));
   return r;
 }
 
 OSQPFloat OSQPVectorf_norm_1(const OSQPVectorf* a) {
   OSQPFloat r;
-  DIST_REDUCE(a->length, r = b200_vec_norm_1(a->d_val, a->length));
+  DIST_REDUCE(a->length, r = b200_vec_norm_1(a->d_val + RED_OFF, RED_CNT));
+  /* the only caller (scaling.c:123-124) divides by the LOCAL n to get a mean over columns: hand it
+     the global sum rescaled so that the quotient is the global mean */
+  if (B200_IS_COLSPLIT(a->length) && b200_dist_nglobal > 0)
+    r = r * (OSQPFloat)a->length / (OSQPFloat)b200_dist_nglobal;
   return r;
 }
 
@@ -338,7 +353,7 @@ OSQPFloat OSQPVectorf_norm_2(const OSQPVectorf* a) { return b200_vec_norm_2(a->d
 OSQPFloat OSQPVectorf_dot_prod(const OSQPVectorf* a, const OSQPVectorf* b) {
   OSQPFloat r;
   int       live = b200_norm_cache_live();
-  DIST_REDUCE(a->length, r = b200_vec_dot(a->d_val, b->d_val, a->length));
+  DIST_REDUCE(a->length, r = b200_vec_dot(a->d_val + RED_OFF, b->d_val + RED_OFF, RED_CNT));
   b200_norm_cache_after(live, OSQP_NULL, 0);
   return r;
 }
@@ -346,7 +361,7 @@ OSQPFloat OSQPVectorf_dot_prod(const OSQPVectorf* a, const OSQPVectorf* b) {
 OSQPFloat OSQPVectorf_dot_prod_signed(const OSQPVectorf* a, const OSQPVectorf* b, OSQPInt sign) {
   OSQPFloat r;
   int       live = b200_norm_cache_live();
-  DIST_REDUCE(a->length, r = b200_vec_dot_signed(a->d_val, b->d_val, (int)sign, a->length));
+  DIST_REDUCE(a->length, r = b200_vec_dot_signed(a->d_val + RED_OFF, b->d_val + RED_OFF, (int)sign, RED_CNT));
   b200_norm_cache_after(live, OSQP_NULL, 0);
   return r;
 }

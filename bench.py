@@ -395,7 +395,7 @@ def run_b200(args):
                        "solver": "indirect: device-resident Jacobi PCG on the reduced KKT system (CUDA-graph WHILE loop of lean sm_100a passes)",
                        "step": "one cold-start osqp_solve to eps 1e-3",
                        "parallelism": ("1 GPU" if world == 1 else
-                                       (f"one QP row-sharded over {world} GPUs, 1 NCCL all-reduce (n doubles) per K.p"
+                                       (f"one QP row-sharded over {world} GPUs, column-split layout: 1 NCCL all-reduce of the shared columns + 2 scalar exchanges per CG iteration"
                                         if sharded else f"{world} independent QPs (same generator and seed), one per GPU, no comms")),
                        "l2_policy": "working set (>=460 MB of matrices per CG iteration) exceeds the 126 MB L2",
                        "settings": {kk: vv for kk, vv in SETTINGS.items()}},

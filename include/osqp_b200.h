@@ -237,6 +237,12 @@ int  b200_dist_rank(void);
  * sum as appropriate) before handing it to the host: set by the backend around reductions over
  * row-sharded vectors */
 void b200_dist_scope(int sharded);
+/* column-split layout (SURVEY.md 8e "recommended refinement"): every n-vector of this rank is
+ * [n_shared columns touched by several ranks, replicated ; the columns this rank owns].  Only the
+ * shared slice is ever exchanged.  n_shared < 0 switches the layout off (plain row sharding with
+ * fully replicated n-vectors). */
+void b200_dist_set_split(int n_shared);
+int  b200_dist_n_shared(void);
 void b200_dist_allreduce_sum(b200_float* d_buf, int n);   /* in place, library stream */
 void b200_dist_allreduce_max(b200_float* d_buf, int n);
 void b200_dist_stats(unsigned long long* n_calls, unsigned long long* bytes);

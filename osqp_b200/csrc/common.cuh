@@ -97,6 +97,9 @@ bool mail_wait(unsigned long long seq);
 // dist.cu
 bool dist_active();
 bool dist_scope();
+bool dist_split();
+int  dist_n_shared();
+int  dist_col_off();
 void dist_allreduce_f64(double* d_buf, int n, bool is_max);
 
 // ------------------------------------------------------------------ device side

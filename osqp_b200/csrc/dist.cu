@@ -30,6 +30,7 @@ struct Dist {
   fn_errstr errstr = nullptr;
   nccl_comm_t comm = nullptr;
   int rank = 0, world = 1, scope = 0;
+  int n_shared = -1;     // >= 0: column-split layout, n-vectors are [shared (replicated) ; local (owned)]
   unsigned long long n_allreduce = 0, bytes_allreduce = 0;
 };
 Dist g;
@@ -70,6 +71,11 @@ namespace b200 {
 // backend declared the operand row-sharded
 bool dist_active() { return g.comm != nullptr && g.world > 1; }
 bool dist_scope() { return dist_active() && g.scope; }
+// column-split layout: every n-vector is [shared columns (replicated on all ranks) ; local columns
+// (owned by this rank)].  A reduction over such a vector counts the shared slice on rank 0 only.
+bool dist_split() { return dist_active() && g.n_shared >= 0; }
+int  dist_n_shared() { return dist_split() ? g.n_shared : 0; }
+int  dist_col_off() { return (dist_split() && g.rank > 0) ? g.n_shared : 0; }
 void dist_allreduce_f64(double* d_buf, int n, bool is_max) {
   if (!dist_active() || n <= 0) return;
   nccl_ok(g.allreduce(d_buf, d_buf, (size_t)n, NCCL_DOUBLE, is_max ? NCCL_MAX : NCCL_SUM, g.comm,
@@ -114,6 +120,8 @@ void b200_dist_finalize(void) {
 int b200_dist_world(void) { return g.world; }
 int b200_dist_rank(void) { return g.rank; }
 void b200_dist_scope(int sharded) { g.scope = sharded; }
+void b200_dist_set_split(int n_shared) { g.n_shared = n_shared; }
+int  b200_dist_n_shared(void) { return g.n_shared; }
 
 void b200_dist_allreduce_sum(T* d_buf, int n) {
   if (!dist_active() || n <= 0) return;

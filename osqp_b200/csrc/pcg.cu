@@ -236,13 +236,16 @@ __global__ void k2_rowptr_kernel(int n, const int* rpP, const int* rpAt, int* rp
 }
 
 // one warp per row: copy P row (sigma added on the diagonal) then A' row (columns shifted by n)
-__global__ void __launch_bounds__(kBlock) k2_fill_kernel(int n, T sigma, T pscale, const int* rpP, const int* ciP,
+__global__ void __launch_bounds__(kBlock) k2_fill_kernel(int n, T sigma, T pscale_head, int n_head, const int* rpP, const int* ciP,
                                                          const T* vP, const int* rpAt, const int* ciAt,
                                                          const T* vAt, const int* rp, int* ci, T* v) {
   const int lane = threadIdx.x & 31;
   const int wpb  = kBlock >> 5;
   for (int row = blockIdx.x * wpb + (threadIdx.x >> 5); row < n; row += gridDim.x * wpb) {
     int dst = rp[row];
+    // rows < n_head (all rows under plain row sharding, the SHARED columns under the column-split
+    // layout) carry P + sigma I on one rank only; rows owned by this rank always carry it
+    const T pscale = row < n_head ? pscale_head : (T)1;
     const int s0 = rpP[row], e0 = rpP[row + 1];
     for (int k = s0 + lane; k < e0; k += 32) {
       const int c = ciP[k];
@@ -373,7 +376,7 @@ void b200_pcg_refresh_matrices(b200_pcg* s) {
   int cap  = c.sm_count * 8;
   if (grid > cap) grid = cap;
   k2_fill_kernel<<<grid, kBlock, 0, c.stream>>>(
-      n, s->sigma, (T)(s->include_P ? 1 : 0), s->P->d_row_ptr, s->P->d_col_ind, s->P->d_val, hasA ? s->At->d_row_ptr : nullptr,
+      n, s->sigma, (T)(s->include_P ? 1 : 0), (s->sharded && dist_split()) ? dist_n_shared() : n, s->P->d_row_ptr, s->P->d_col_ind, s->P->d_val, hasA ? s->At->d_row_ptr : nullptr,
       hasA ? s->At->d_col_ind : nullptr, hasA ? s->At->d_val : nullptr, s->K2.d_row_ptr,
       s->K2.d_col_ind, s->K2.d_val);
   count_launch();
@@ -388,7 +391,7 @@ void b200_pcg_refresh_precond(b200_pcg* s) {
   // row-sharded: diag(A' R A) = sum over ranks of the local column sums
   if (s->sharded && s->precond) {
     if (s->m <= 0) B200_CHECK(cudaMemsetAsync(s->d_ad, 0, sizeof(T) * n, c.stream));
-    b200_dist_allreduce_sum(s->d_ad, n);
+    b200_dist_allreduce_sum(s->d_ad, dist_split() ? dist_n_shared() : n);
   }
   precond_kernel<<<ew_grid(n), kBlock, 0, c.stream>>>(n, s->sigma, s->d_pd, s->d_ad, s->d_minv, s->precond);
   count_launch();

@@ -47,6 +47,7 @@ struct PcgArgs {
 // running scalars of one solve in the graph driver (device memory)
 struct PcgRun {
   double   eps, rTy, rnorm, pKp, beta, rhs_norm, alpha;
+  double   dots[3];      // p'Kp, r'M^-1 Kp, Kp'M^-1 Kp (sharded driver: exchanged between the ranks)
   double   rf, eps_prev;
   int      it, zero_iters;
   unsigned ticket[SLOT_COUNT];

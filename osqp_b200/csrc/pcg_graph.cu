@@ -60,6 +60,59 @@ __device__ __forceinline__ double fold(const double* red, int stride, int slot, 
   return IS_MAX ? block_max(a, shr) : block_sum(a, shr);
 }
 
+// sums of three values over the CTA with one pair of barriers; results valid in thread 0
+__device__ __forceinline__ void block_sum3(double& a, double& b, double& c, double* sh /* >= 3*16 */) {
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  a = warp_sum(a); b = warp_sum(b); c = warp_sum(c);
+  if (lane == 0) { sh[w] = a; sh[16 + w] = b; sh[32 + w] = c; }
+  __syncthreads();
+  if (w == 0) {
+    const int nw = blockDim.x >> 5;
+    a = warp_sum(lane < nw ? sh[lane] : 0.0);
+    b = warp_sum(lane < nw ? sh[16 + lane] : 0.0);
+    c = warp_sum(lane < nw ? sh[32 + lane] : 0.0);
+  }
+}
+__device__ __forceinline__ void block_sum_max(double& a, double& mx, double* sh) {
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  a = warp_sum(a); mx = warp_max(mx);
+  if (lane == 0) { sh[w] = a; sh[16 + w] = mx; }
+  __syncthreads();
+  if (w == 0) {
+    const int nw = blockDim.x >> 5;
+    a  = warp_sum(lane < nw ? sh[lane] : 0.0);
+    mx = warp_max(lane < nw ? sh[16 + lane] : 0.0);
+  }
+}
+
+// thread 0 publishes up to three partials of this CTA; the last CTA to arrive folds every slot in
+// index order.  Returns true in all threads of that CTA, totals valid in all its threads.
+template <int NSLOT, bool LAST_IS_MAX>
+__device__ __forceinline__ bool publish_fold(const double* part, const int* slots, double* red, int stride,
+                                             unsigned* ticket, double* shr, double* totals) {
+  __shared__ int s_last;
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int i = 0; i < NSLOT; i++) red[slots[i] * stride + blockIdx.x] = part[i];
+    __threadfence();
+    s_last = (atomicAdd(ticket, 1u) == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (!s_last) return false;
+  __threadfence();
+#pragma unroll
+  for (int i = 0; i < NSLOT; i++) {
+    const bool is_max = LAST_IS_MAX && (i == NSLOT - 1);
+    double acc = 0.0;
+    for (int j = threadIdx.x; j < (int)gridDim.x; j += blockDim.x) {
+      const double v = __ldcg(red + slots[i] * stride + j);
+      acc = is_max ? fmax(acc, v) : acc + v;
+    }
+    totals[i] = is_max ? block_max(acc, shr) : block_sum(acc, shr);
+  }
+  return true;
+}
+
 // The argument block of the current solve lives in CONSTANT memory: every kernel of the driver
 // (the graph's kernel nodes have frozen parameters) reads pointers and scalars as constant-bank
 // operands -- no registers, no L1 traffic.  (Reading them through a pointer to global memory cost
@@ -271,11 +324,11 @@ __global__ void __launch_bounds__(kSpmvBlock, B200_SPMV_MINBLOCKS) g_pass_At(con
 
 // row-sharded: ||b1 + Kp||_inf -> run->rhs_norm   (Kp = all-reduced A'(rho .* b2))
 __global__ void __launch_bounds__(kBlock) g_rhs_norm_sum(const PcgArgs* ap, PcgRun* run, double* red,
-                                                         int stride, int have_At) {
+                                                         int stride, int have_At, int off) {
   __shared__ double shr[33];
   const PcgArgs& a = c_args;
   double mx = 0.0;
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < a.n; i += gridDim.x * blockDim.x)
+  for (int i = off + blockIdx.x * blockDim.x + threadIdx.x; i < a.n; i += gridDim.x * blockDim.x)
     mx = fmax(mx, fabs((double)(a.b[i] + (have_At ? a.Kp[i] : (T)0))));
   mx = block_max(mx, shr);
   double tot;
@@ -288,7 +341,7 @@ __global__ void __launch_bounds__(kBlock) g_rhs_norm_sum(const PcgArgs* ap, PcgR
 // row-sharded P2 tail: r = Kp - b1 ; p = -M^-1 r ; totals r'y, ||r||_inf (n-vectors are replicated,
 // so every rank computes the same totals and no scalar exchange is needed)
 __global__ void __launch_bounds__(kBlock) g_resid_init(const PcgArgs* ap, PcgRun* run, double* red,
-                                                       int stride) {
+                                                       int stride, int off) {
   __shared__ double shr[33];
   const PcgArgs& a = c_args;
   double acc0 = 0.0, acc1 = 0.0;
@@ -297,8 +350,10 @@ __global__ void __launch_bounds__(kBlock) g_resid_init(const PcgArgs* ap, PcgRun
     const T yy = a.minv[i] * rr;
     a.r[i] = rr;
     a.p[i] = -yy;
-    acc0 += (double)rr * (double)yy;
-    acc1 = fmax(acc1, fabs((double)rr));
+    if (i >= off) {       // column split: the shared slice is counted by rank 0 only
+      acc0 += (double)rr * (double)yy;
+      acc1 = fmax(acc1, fabs((double)rr));
+    }
   }
   acc0 = block_sum(acc0, shr);
   acc1 = block_max(acc1, shr);
@@ -314,19 +369,35 @@ __global__ void __launch_bounds__(kBlock) g_resid_init(const PcgArgs* ap, PcgRun
   }
 }
 
-// row-sharded L2 tail: p'Kp of the all-reduced Kp
-__global__ void __launch_bounds__(kBlock) g_dot_pKp(const PcgArgs* ap, PcgRun* run, double* red, int stride) {
-  __shared__ double shr[33];
+// row-sharded L2 tail: the three dots of the exchanged Kp (p'Kp, r'M^-1 Kp, Kp'M^-1 Kp) over the
+// columns this rank counts; summed over the ranks afterwards when the layout is column-split
+__global__ void __launch_bounds__(kBlock) g_dots3(const PcgArgs* ap, PcgRun* run, double* red, int stride, int off) {
+  __shared__ double shr[48];
   const PcgArgs& a = c_args;
-  double acc = 0.0;
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < a.n; i += gridDim.x * blockDim.x)
-    acc += (double)a.p[i] * (double)a.Kp[i];
-  acc = block_sum(acc, shr);
-  double tot;
-  if (publish<false>(acc, red, stride, SLOT_PKP, &run->ticket[SLOT_PKP], true, shr, tot) && threadIdx.x == 0) {
-    run->pKp = tot;
+  double acc = 0.0, acc1 = 0.0, acc2 = 0.0;
+  for (int i = off + blockIdx.x * blockDim.x + threadIdx.x; i < a.n; i += gridDim.x * blockDim.x) {
+    const T kp = a.Kp[i];
+    const T yk = a.minv[i] * kp;
+    acc  += (double)a.p[i] * (double)kp;
+    acc1 += (double)a.r[i] * (double)yk;
+    acc2 += (double)kp * (double)yk;
+  }
+  block_sum3(acc, acc1, acc2, shr);
+  const double part[3] = {acc, acc1, acc2};
+  const int slots[3] = {SLOT_PKP, SLOT_RKP, SLOT_KPKP};
+  double tot[3];
+  if (publish_fold<3, false>(part, slots, red, stride, &run->ticket[SLOT_PKP], shr, tot) && threadIdx.x == 0) {
+    run->dots[0] = tot[0];
+    run->dots[1] = tot[1];
+    run->dots[2] = tot[2];
     run->ticket[SLOT_PKP] = 0;
   }
+}
+// alpha, beta from the (exchanged) dots
+__global__ void g_step_scalars(PcgRun* run) {
+  if (threadIdx.x || blockIdx.x) return;
+  run->pKp = run->dots[0];
+  cg_step_scalars(run, run->dots[0], run->dots[1], run->dots[2]);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -345,59 +416,6 @@ __global__ void __launch_bounds__(kBlock) g_dot_pKp(const PcgArgs* ap, PcgRun* r
 constexpr int kLeanBlock = 512;
 constexpr int kLeanCtasPerSm = 3;
 static_assert(kTile == 4 * kLeanBlock, "lean pass assumes one batch of 4 per thread");
-
-// sums of three values over the CTA with one pair of barriers; results valid in thread 0
-__device__ __forceinline__ void block_sum3(double& a, double& b, double& c, double* sh /* >= 3*16 */) {
-  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  a = warp_sum(a); b = warp_sum(b); c = warp_sum(c);
-  if (lane == 0) { sh[w] = a; sh[16 + w] = b; sh[32 + w] = c; }
-  __syncthreads();
-  if (w == 0) {
-    const int nw = blockDim.x >> 5;
-    a = warp_sum(lane < nw ? sh[lane] : 0.0);
-    b = warp_sum(lane < nw ? sh[16 + lane] : 0.0);
-    c = warp_sum(lane < nw ? sh[32 + lane] : 0.0);
-  }
-}
-__device__ __forceinline__ void block_sum_max(double& a, double& mx, double* sh) {
-  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  a = warp_sum(a); mx = warp_max(mx);
-  if (lane == 0) { sh[w] = a; sh[16 + w] = mx; }
-  __syncthreads();
-  if (w == 0) {
-    const int nw = blockDim.x >> 5;
-    a  = warp_sum(lane < nw ? sh[lane] : 0.0);
-    mx = warp_max(lane < nw ? sh[16 + lane] : 0.0);
-  }
-}
-
-// thread 0 publishes up to three partials of this CTA; the last CTA to arrive folds every slot in
-// index order.  Returns true in all threads of that CTA, totals valid in all its threads.
-template <int NSLOT, bool LAST_IS_MAX>
-__device__ __forceinline__ bool publish_fold(const double* part, const int* slots, double* red, int stride,
-                                             unsigned* ticket, double* shr, double* totals) {
-  __shared__ int s_last;
-  if (threadIdx.x == 0) {
-#pragma unroll
-    for (int i = 0; i < NSLOT; i++) red[slots[i] * stride + blockIdx.x] = part[i];
-    __threadfence();
-    s_last = (atomicAdd(ticket, 1u) == gridDim.x - 1);
-  }
-  __syncthreads();
-  if (!s_last) return false;
-  __threadfence();
-#pragma unroll
-  for (int i = 0; i < NSLOT; i++) {
-    const bool is_max = LAST_IS_MAX && (i == NSLOT - 1);
-    double acc = 0.0;
-    for (int j = threadIdx.x; j < (int)gridDim.x; j += blockDim.x) {
-      const double v = __ldcg(red + slots[i] * stride + j);
-      acc = is_max ? fmax(acc, v) : acc + v;
-    }
-    totals[i] = is_max ? block_max(acc, shr) : block_sum(acc, shr);
-  }
-  return true;
-}
 
 template <int MODE>
 __global__ void __launch_bounds__(kLeanBlock, kLeanCtasPerSm) g_lean_pass(const PcgArgs* ap, PcgRun* run, double* red,
@@ -574,7 +592,7 @@ __global__ void __launch_bounds__(kBlock) g_direction(const PcgArgs* ap, const P
 // L3+L4 in one kernel (graph driver): x += a p ; r += a Kp ; p = beta p - M^-1 r ; Ax += a w ;
 // totals r'y (exact), ||r||_inf ; last CTA: it++, loop condition.  8 n F + 3 m F bytes.
 __global__ void __launch_bounds__(kBlock) g_update_fused(const PcgArgs* ap, PcgRun* run, double* red, int stride,
-                                                         cudaGraphConditionalHandle h) {
+                                                         cudaGraphConditionalHandle h, int off) {
   __shared__ double shr[33];
   const PcgArgs& a = c_args;
   const int n = a.n, m = a.m;
@@ -590,8 +608,10 @@ __global__ void __launch_bounds__(kBlock) g_update_fused(const PcgArgs* ap, PcgR
     r[i] = rr;
     const T yy = minv[i] * rr;
     p[i] = beta * pi - yy;
-    acc_rty += (double)rr * (double)yy;
-    acc_max = fmax(acc_max, fabs((double)rr));
+    if (i >= off) {      // column-split layout: the shared slice is counted by rank 0 only
+      acc_rty += (double)rr * (double)yy;
+      acc_max = fmax(acc_max, fabs((double)rr));
+    }
   }
   T* __restrict__ Ax = a.Ax; const T* __restrict__ w = a.w;
   for (int j = gtid; j < m; j += gstride) Ax[j] += alpha * w[j];
@@ -743,7 +763,8 @@ int b200_pcg_graph_build(b200_pcg* s) {
   }
   {
     // L3 + L4 in one kernel: alpha AND beta are known after the fused-operator pass
-    void* a3[] = {(void*)&d_args, (void*)&d_run, (void*)&d_red, (void*)&stride, (void*)&h};
+    int zero_off = 0;
+    void* a3[] = {(void*)&d_args, (void*)&d_run, (void*)&d_red, (void*)&stride, (void*)&h, (void*)&zero_off};
     int nm = s->n > s->m ? s->n : s->m;
     int gu = ew_grid(nm) < cap ? ew_grid(nm) : cap;
     add((void*)g_update_fused, dim3(gu), dim3(kBlock), 0, a3);
@@ -815,7 +836,7 @@ int b200_pcg_graph_solve(b200_pcg* s, const PcgArgs& a) {
       if (s->lean) g_lean_pass<1><<<lean_grid(s->K2), kLeanBlock, 0, st>>>(d_args, s->d_run, s->d_gred, cap);
       else g_pass_K<1><<<pass_grid(s->K2, cap), kSpmvBlock, kSpmvSmemBytes, st>>>(d_args, s->d_run, s->d_gred, cap);
       count_launch("L2 pass K2");
-      g_update_fused<<<gu, kBlock, 0, st>>>(d_args, s->d_run, s->d_gred, cap, none);
+      g_update_fused<<<gu, kBlock, 0, st>>>(d_args, s->d_run, s->d_gred, cap, none, 0);
       count_launch("L3+L4 update");
     }
   } else {
@@ -829,18 +850,33 @@ int b200_pcg_graph_solve(b200_pcg* s, const PcgArgs& a) {
 }
 
 // ------------------------------------------------------------------ row-sharded driver
-// Every rank holds a row block A_r (CSR), A_r' and the matching slices of the m-vectors; x, p, r,
-// Kp, M^-1 are replicated.  K p = (P + sigma I) p [rank 0 only] + A_r' (rho .* (A_r p)) summed by ONE
-// NCCL all-reduce of the length-n partial per CG iteration; all CG scalars are then computed
-// redundantly from replicated vectors, so they are bit-identical on every rank and the ranks take
-// the same branch without any scalar exchange.  The loop is driven by the host, which reads
-// (||r||_inf, eps, it) back once per iteration.
+// Every rank holds a row block A_r (CSR), A_r' and the matching slices of the m-vectors.
+//   * plain row sharding: the n-vectors x, p, r, Kp, M^-1 are replicated; K p = (P + sigma I) p
+//     [rank 0 only] + A_r' (rho .* (A_r p)) summed by one all-reduce of the length-n partial per CG
+//     iteration; every CG scalar is then computed redundantly from replicated vectors.
+//   * column-split layout (dist_split()): the n-vectors are [shared ; local]; only
+//     the SHARED slice of the partial K p is all-reduced (the local columns are complete on their
+//     owner, which also carries their P + sigma I), and the CG scalars -- sums over shared columns
+//     once plus every rank's local columns -- take two small all-reduces per iteration (the three
+//     dots that fix alpha and beta; then r'y and ||r||_inf of the updated residual).
+// The loop is driven by the host, which reads (||r||_inf, eps, it) back once per iteration.
+namespace {
+inline void exchange_vector(T* d_v, int n) {
+  b200_dist_allreduce_sum(d_v, dist_split() ? dist_n_shared() : n);
+}
+// scalars of `run` that were reduced over this rank's columns only
+inline void exchange_scalars(double* d_first, int count, bool is_max) {
+  if (dist_split()) dist_allreduce_f64(d_first, count, is_max);
+}
+}  // namespace
+
 int b200_pcg_sharded_solve(b200_pcg* s, const PcgArgs& a) {
   Context& c = ctx();
   cudaStream_t st = c.stream;
   const int cap = s->gred_stride;
   const int n = s->n, m = s->m;
   const int gn = ew_grid(n) < cap ? ew_grid(n) : cap;
+  const int off = dist_col_off();
   set_args(a, st);
   ctx().epoch++;
   const PcgArgs* d_args = s->d_args;
@@ -856,9 +892,10 @@ int b200_pcg_sharded_solve(b200_pcg* s, const PcgArgs& a) {
     } else {
       B200_CHECK(cudaMemsetAsync(s->d_Kp, 0, sizeof(T) * n, st));
     }
-    b200_dist_allreduce_sum(s->d_Kp, n);
-    g_rhs_norm_sum<<<gn, kBlock, 0, st>>>(d_args, run, s->d_gred, cap, 1);
+    exchange_vector(s->d_Kp, n);
+    g_rhs_norm_sum<<<gn, kBlock, 0, st>>>(d_args, run, s->d_gred, cap, 1, off);
     count_launch();
+    exchange_scalars(&run->rhs_norm, 1, true);
   }
   g_tolerance<<<1, 32, 0, st>>>(d_args, run);
   count_launch();
@@ -869,12 +906,16 @@ int b200_pcg_sharded_solve(b200_pcg* s, const PcgArgs& a) {
   }
   g_pass_K<2><<<pass_grid(s->K2, cap), kSpmvBlock, kSpmvSmemBytes, st>>>(d_args, run, s->d_gred, cap);
   count_launch();
-  b200_dist_allreduce_sum(s->d_Kp, n);
-  g_resid_init<<<gn, kBlock, 0, st>>>(d_args, run, s->d_gred, cap);
+  exchange_vector(s->d_Kp, n);
+  g_resid_init<<<gn, kBlock, 0, st>>>(d_args, run, s->d_gred, cap, off);
   count_launch();
+  exchange_scalars(&run->rTy, 1, false);
+  exchange_scalars(&run->rnorm, 1, true);
 
   PcgRun h;
   bool ok = true;
+  const int nm = n > m ? n : m;
+  const int gu = ew_grid(nm) < cap ? ew_grid(nm) : cap;
   for (;;) {
     ok &= B200_CHECK(cudaMemcpyAsync(&h, run, sizeof(PcgRun), cudaMemcpyDeviceToHost, st));
     ok &= B200_CHECK(cudaStreamSynchronize(st));
@@ -885,16 +926,17 @@ int b200_pcg_sharded_solve(b200_pcg* s, const PcgArgs& a) {
     }
     g_pass_K<3><<<pass_grid(s->K2, cap), kSpmvBlock, kSpmvSmemBytes, st>>>(d_args, run, s->d_gred, cap);
     count_launch();
-    b200_dist_allreduce_sum(s->d_Kp, n);
-    g_dot_pKp<<<gn, kBlock, 0, st>>>(d_args, run, s->d_gred, cap);
+    exchange_vector(s->d_Kp, n);
+    g_dots3<<<gn, kBlock, 0, st>>>(d_args, run, s->d_gred, cap, off);
     count_launch();
-    const int nm = n > m ? n : m;
-    g_update<<<ew_grid(nm) < cap ? ew_grid(nm) : cap, kBlock, 0, st>>>(d_args, run, s->d_gred, cap, none);
+    exchange_scalars(run->dots, 3, false);
+    g_step_scalars<<<1, 32, 0, st>>>(run);
     count_launch();
-    g_direction<<<ew_grid(n), kBlock, 0, st>>>(d_args, run);
+    g_update_fused<<<gu, kBlock, 0, st>>>(d_args, run, s->d_gred, cap, none, off);
     count_launch();
+    exchange_scalars(&run->rTy, 1, false);
+    exchange_scalars(&run->rnorm, 1, true);
   }
-  const int nm = n > m ? n : m;
   g_epilogue<<<ew_grid(nm), kBlock, 0, st>>>(d_args, run);
   count_launch();
   return ok ? 0 : 1;
@@ -939,7 +981,7 @@ extern "C" int b200_pcg_profile_last(int reps, double* out_us, int nout) {
   };
   auto passA  = [&] { if (m > 0) g_lean_pass<0><<<lean_grid(*s->A, false), kLeanBlock, 0, st>>>(d_args, run, red, cap); };
   auto passK  = [&] { g_lean_pass<1><<<lean_grid(s->K2), kLeanBlock, 0, st>>>(d_args, run, red, cap); };
-  auto upd    = [&] { g_update_fused<<<gu, kBlock, 0, st>>>(d_args, run, red, cap, none); };
+  auto upd    = [&] { g_update_fused<<<gu, kBlock, 0, st>>>(d_args, run, red, cap, none, 0); };
   out_us[0]  = timeit(passA);
   out_us[1]  = timeit(passK);
   out_us[2]  = timeit(upd);

@@ -291,6 +291,7 @@ struct ResArgs {
   const T *x, *y, *z, *Ax, *Px, *Aty, *q, *l, *u, *Einv, *Dinv;
   T infval, deadzone;
   int n, m;
+  int n_off;     // column-split layout: first n-entry this rank counts (shared slice: rank 0 only)
 };
 
 __device__ __forceinline__ bool res_is_sum(int s) {
@@ -328,7 +329,7 @@ __global__ void __launch_bounds__(kBlock) residuals_kernel(ResArgs a, double* pa
     if (dabs(yp) < (double)a.deadzone) yp = 0.0;
     v[B200_RES_SC] += hi * (yp > 0.0 ? yp : 0.0) + lo * (yp < 0.0 ? yp : 0.0);
   }
-  for (int i = gtid; i < a.n; i += stride) {
+  for (int i = a.n_off + gtid; i < a.n; i += stride) {
     const double q = a.q[i], Px = a.Px[i], Aty = a.m > 0 ? (double)a.Aty[i] : 0.0;
     const double dv = a.Dinv ? (double)a.Dinv[i] : 1.0, x = a.x[i];
     double r = q + Px;
@@ -396,7 +397,7 @@ extern "C" void b200_admm_residuals(const T* x, const T* y, const T* z, const T*
                                     const T* Aty, const T* q, const T* l, const T* u, const T* Einv,
                                     const T* Dinv, T infval, T deadzone, int n, int m, double* h_out) {
   Context& c = ctx();
-  ResArgs a{x, y, z, Ax, Px, Aty, q, l, u, Einv, Dinv, infval, deadzone, n, m};
+  ResArgs a{x, y, z, Ax, Px, Aty, q, l, u, Einv, Dinv, infval, deadzone, n, m, dist_col_off()};
   const int nm = n > m ? n : m;
   int grid = ew_grid(nm);
   if (grid > kMaxRedBlocks) grid = kMaxRedBlocks;
@@ -416,6 +417,11 @@ extern "C" void b200_admm_residuals(const T* x, const T* y, const T* z, const T*
     // them; the n-vector slots are replicated and identical on every rank
     dist_allreduce_f64(c.d_scalar + B200_RES_PRIM_S, B200_RES_SC - B200_RES_PRIM_S, true);
     dist_allreduce_f64(c.d_scalar + B200_RES_SC, 1, false);
+    if (dist_split()) {
+      // column-split layout: the n-vector slots are partial too (maxima, then the two sums)
+      dist_allreduce_f64(c.d_scalar + B200_RES_DUAL_S, B200_RES_XPX - B200_RES_DUAL_S, true);
+      dist_allreduce_f64(c.d_scalar + B200_RES_XPX, 2, false);
+    }
   }
   B200_CHECK(cudaMemcpyAsync(c.h_scalar, c.d_scalar, sizeof(double) * B200_RES_COUNT,
                              cudaMemcpyDeviceToHost, c.stream));

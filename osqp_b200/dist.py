@@ -196,22 +196,61 @@ def init_sharded(dist, local_rank, precision="f64"):
 
 
 class ShardedOSQP(OSQP):
-    """OSQP solver object over a row-sharded problem.  `setup` takes the FULL problem on every
-    rank and keeps this rank's row block; `solve` returns x (replicated) and the local slice of y."""
+    """OSQP solver object over ONE QP whose rows of A are split over the ranks.
 
-    def __init__(self, rank, world, precision="f64"):
+    layout="split" (default): column-split layout -- rows linked through low-degree columns are kept
+    together, every rank solves over [shared columns ; the columns only it touches], and only the
+    shared slice is ever exchanged (plan_column_split).  layout="rows": plain contiguous row blocks
+    with every n-vector replicated.  `setup` takes the FULL problem on every rank; `solve` returns
+    this rank's slice of the solution, `gather` assembles the global (x, y)."""
+
+    def __init__(self, rank, world, precision="f64", layout="split"):
         super().__init__(precision)
-        self.rank, self.world = rank, world
+        self.rank, self.world, self.layout = rank, world, layout
+        self.plan = None
         self._lib.osqp_b200_dist_configure.argtypes = [C.c_int, C.c_int]
         self._lib.osqp_b200_dist_configure.restype = C.c_int
+        self._lib.osqp_b200_dist_configure_split.argtypes = [C.c_int] * 4
+        self._lib.osqp_b200_dist_configure_split.restype = C.c_int
 
     def setup(self, P, q, A, l, u, **settings):
-        sh = shard_problem(dict(P=P, q=q, A=A, l=l, u=u), self.rank, self.world)
-        self.rows, self.bounds = sh["rows"], sh["bounds"]
-        n = sp.csc_matrix(P).shape[0]
-        if self._lib.osqp_b200_dist_configure(n, sh["A"].shape[0]) != 0:
-            raise ValueError("a row block may not have exactly n rows")
+        pb = dict(P=P, q=q, A=A, l=l, u=u)
+        self.n_global, self.m_global = sp.csc_matrix(P).shape[0], sp.csc_matrix(A).shape[0]
+        if self.layout == "split":
+            self.plan = plan_column_split(P, A, self.world)
+            sh = shard_problem_split(pb, self.rank, self.plan)
+            self.padded = sh["padded"]
+            self.n_shared = sh["n_shared"]
+            rc = self._lib.osqp_b200_dist_configure_split(sh["A"].shape[1], sh["A"].shape[0], self.n_shared,
+                                                          self.n_global)
+            if rc != 0:
+                raise ValueError("invalid column-split layout for this rank")
+        else:
+            sh = shard_problem(pb, self.rank, self.world)
+            self.rows, self.bounds = sh["rows"], sh["bounds"]
+            if self._lib.osqp_b200_dist_configure(self.n_global, sh["A"].shape[0]) != 0:
+                raise ValueError("a row block may not have exactly n rows")
         return super().setup(sh["P"], sh["q"], sh["A"], sh["l"], sh["u"], **settings)
+
+    def gather(self, r, dist):
+        """Global (x, y) from the per-rank results `r` (collective; every rank gets the same arrays)."""
+        parts = [None] * self.world
+        dist.all_gather_object(parts, (np.asarray(r.x), np.asarray(r.y)))
+        x, y = np.zeros(self.n_global), np.zeros(self.m_global)
+        if self.plan is not None:
+            for rk, (xr, yr) in enumerate(parts):
+                rows, cols = self.plan["rows"][rk], self.plan["cols"][rk]
+                ns = self.plan["shared"].size
+                if rk == 0:
+                    x[cols] = xr
+                else:
+                    x[cols[ns:]] = xr[ns:]
+                y[rows] = yr[:len(rows)]
+        else:
+            x[:] = parts[0][0]
+            for rk, (_, yr) in enumerate(parts):
+                y[int(self.bounds[rk]):int(self.bounds[rk + 1])] = yr
+        return x, y
 
     def cleanup(self):
         super().cleanup()

@@ -22,15 +22,18 @@ def _ngpus():
 
 
 @pytest.mark.skipif(_ngpus() < 2, reason="needs 2 GPUs")
+@pytest.mark.parametrize("layout", ["split", "rows"])
 @pytest.mark.parametrize("family", ["lasso", "portfolio", "huber", "svm"])
-def test_two_rank_sharded_solve_matches_oracle(family):
+def test_two_rank_sharded_solve_matches_oracle(family, layout):
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
            "--master-addr", "127.0.0.1", "--master-port", "29541", str(ROOT / "tools" / "sharded_worker.py"),
-           "--family", family, "--scale", "0.003", "--check"]
+           "--family", family, "--scale", "0.003", "--check", "--layout", layout]
     out = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=dict(os.environ, MASTER_ADDR="127.0.0.1"))
     line = [l for l in out.stdout.splitlines() if l.startswith("SHARDED ")]
     assert line, out.stdout[-1500:] + out.stderr[-1500:]
     res = json.loads(line[0][len("SHARDED "):])
     assert res["PARITY"] == "OK", res
     assert res["allreduce_calls"] > res["cg_iters"]          # one exchange per K.p (+ residual checks)
+    if layout == "split" and family != "portfolio":         # epigraph families: only the features are shared
+        assert res["n_shared"] < 0.2 * res["n"], res
     assert "REPLICATED_X_IDENTICAL True" in out.stdout

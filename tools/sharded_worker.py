@@ -17,6 +17,7 @@ ap.add_argument("--scale", type=float, default=0.01)
 ap.add_argument("--eps", type=float, default=1e-3)
 ap.add_argument("--check", action="store_true")
 ap.add_argument("--reps", type=int, default=1)
+ap.add_argument("--layout", default="split", choices=["split", "rows"])
 args = ap.parse_args()
 
 local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -42,7 +43,7 @@ kw = dict(eps_abs=args.eps, eps_rel=args.eps, rho_is_vec=0, adaptive_rho_toleran
 if args.check:
     kw.update(eps_abs=1e-6, eps_rel=1e-6, cg_tol_fraction=1e-8, cg_max_iter=500, max_iter=20000)
 
-prob = ShardedOSQP(rank, world)
+prob = ShardedOSQP(rank, world, layout=args.layout)
 t0 = time.perf_counter(); prob.setup(pb["P"], pb["q"], pb["A"], pb["l"], pb["u"], **kw); t1 = time.perf_counter()
 best = None
 for rep in range(args.reps):
@@ -51,16 +52,16 @@ for rep in range(args.reps):
     tmax = torch.tensor([tb - ta], device="cuda", dtype=torch.float64); dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
     best = tmax.item() if best is None else min(best, tmax.item())
 cg, ns = prob.cg_stats()
-ys = [torch.zeros(int(b1 - b0), dtype=torch.float64, device="cuda") for b0, b1 in zip(prob.bounds[:-1], prob.bounds[1:])]
-dist.all_gather(ys, torch.from_numpy(r.y).cuda())
-y = torch.cat(ys).cpu().numpy()
+x, y = prob.gather(r, dist)
 ncalls = __import__("ctypes").c_ulonglong(0); nbytes = __import__("ctypes").c_ulonglong(0)
 k.b200_dist_stats(__import__("ctypes").byref(ncalls), __import__("ctypes").byref(nbytes))
 if rank == 0:
     out = dict(family=args.family, n=n, m=m, nnzA=int(pb["A"].nnz), world=world, status=r.info.status, iters=r.info.iter,
                obj=r.info.obj_val, prim_res=r.info.prim_res, dual_res=r.info.dual_res, cg_iters=cg, solves=ns,
                setup_s=t1 - t0, solve_s=best, iters_per_s=r.info.iter / best, allreduce_calls=ncalls.value,
-               allreduce_MB=nbytes.value / 1e6)
+               allreduce_MB=nbytes.value / 1e6, layout=args.layout,
+               n_shared=(int(prob.plan["shared"].size) if prob.plan is not None else n),
+               n_local=int(prob.n), m_local=int(prob.m))
     if args.check:
         from osqp_b200.interface import OSQP as G, LoadedLibrary
         root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -69,14 +70,17 @@ if rank == 0:
             pb["P"], pb["q"], pb["A"], pb["l"], pb["u"], **kwo).solve()
         out.update(oracle_status=ro.info.status, oracle_iters=ro.info.iter, oracle_obj=ro.info.obj_val,
                    obj_rel_err=abs(r.info.obj_val - ro.info.obj_val) / max(1.0, abs(ro.info.obj_val)),
-                   x_err=float(np.abs(r.x - ro.x).max()), y_err=float(np.abs(y - ro.y).max()))
+                   x_err=float(np.abs(x - ro.x).max()), y_err=float(np.abs(y - ro.y).max()))
         ok = (out["status"] == out["oracle_status"] and out["obj_rel_err"] <= 1e-6 and
               out["x_err"] <= 1e-4 * max(1.0, np.abs(ro.x).max()) and
               abs(out["iters"] - ro.info.iter) <= max(0.1 * ro.info.iter, 50))
         out["PARITY"] = "OK" if ok else "FAIL"
     print("SHARDED " + json.dumps(out), flush=True)
-# every rank must hold the same x (replicated) -- checksum of checksums
-xs = torch.tensor([float(np.sum(r.x)), float(np.abs(r.x).max())], device="cuda", dtype=torch.float64)
+# every rank must hold the same replicated entries of x (all of x under plain row sharding, the
+# shared slice under the column split) -- checksum of checksums
+ns = int(prob.plan["shared"].size) if prob.plan is not None else n
+rep = np.asarray(r.x)[:ns]
+xs = torch.tensor([float(np.sum(rep)), float(np.abs(rep).max()) if ns else 0.0], device="cuda", dtype=torch.float64)
 lo, hi = xs.clone(), xs.clone()
 dist.all_reduce(lo, op=dist.ReduceOp.MIN); dist.all_reduce(hi, op=dist.ReduceOp.MAX)
 if rank == 0:
