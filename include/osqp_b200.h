@@ -47,6 +47,9 @@ void b200_sync(void);                    /* wait for the library stream         
 void* b200_stream_handle(void);          /* cudaStream_t of the library stream      */
 int  b200_last_error(void);              /* sticky CUDA error code, 0 if none       */
 unsigned long long b200_launch_count(void); /* kernels launched since b200_init      */
+/* launch tracer (development aid): with B200_TRACE_FILE set, every launch / collective records a
+ * CUDA event + host time, dumped as CSV at b200_shutdown; this adds a named marker */
+void b200_trace_mark(const char* tag);
 /* CUDA-event timing on the library stream (bench.py / profiling only) */
 void* b200_event_create(void);
 void  b200_event_destroy(void* ev);

@@ -173,6 +173,10 @@ unsigned long long b200_launch_count(void) { return ctx().launches; }
 
 unsigned long long b200_epoch(void) { return ctx().epoch; }
 
+void b200_trace_mark(const char* tag) {
+  if (ctx().trace_on) trace_point(strdup(tag ? tag : "mark"));   // tags live until the dump
+}
+
 void* b200_event_create(void) {
   cudaEvent_t e = nullptr;
   if (!B200_CHECK(cudaEventCreate(&e))) return nullptr;

@@ -80,6 +80,7 @@ void dist_allreduce_f64(double* d_buf, int n, bool is_max) {
   if (!dist_active() || n <= 0) return;
   nccl_ok(g.allreduce(d_buf, d_buf, (size_t)n, NCCL_DOUBLE, is_max ? NCCL_MAX : NCCL_SUM, g.comm,
                       ctx().stream), "ncclAllReduce(f64)");
+  if (ctx().trace_on) trace_point(n <= 4 ? "allreduce(scalars)" : "allreduce(f64 block)");
   g.n_allreduce++;
   g.bytes_allreduce += (unsigned long long)n * 8;
 }
@@ -128,6 +129,7 @@ void b200_dist_allreduce_sum(T* d_buf, int n) {
   ctx().epoch++;
   nccl_ok(g.allreduce(d_buf, d_buf, (size_t)n, sizeof(T) == 8 ? NCCL_DOUBLE : NCCL_FLOAT, NCCL_SUM, g.comm,
                       ctx().stream), "ncclAllReduce(sum)");
+  if (ctx().trace_on) trace_point("allreduce(vector sum)");
   g.n_allreduce++;
   g.bytes_allreduce += (unsigned long long)n * sizeof(T);
 }
@@ -137,6 +139,7 @@ void b200_dist_allreduce_max(T* d_buf, int n) {
   ctx().epoch++;
   nccl_ok(g.allreduce(d_buf, d_buf, (size_t)n, sizeof(T) == 8 ? NCCL_DOUBLE : NCCL_FLOAT, NCCL_MAX, g.comm,
                       ctx().stream), "ncclAllReduce(max)");
+  if (ctx().trace_on) trace_point("allreduce(vector max)");
   g.n_allreduce++;
   g.bytes_allreduce += (unsigned long long)n * sizeof(T);
 }

@@ -48,6 +48,7 @@ struct PcgArgs {
 struct PcgRun {
   double   eps, rTy, rnorm, pKp, beta, rhs_norm, alpha;
   double   dots[3];      // p'Kp, r'M^-1 Kp, Kp'M^-1 Kp (sharded driver: exchanged between the ranks)
+  double   slots[16];    // column-split layout: (r'y, ||r||_inf) of every rank, gathered by ONE sum all-reduce
   double   rf, eps_prev;
   int      it, zero_iters;
   unsigned ticket[SLOT_COUNT];

@@ -393,6 +393,26 @@ __global__ void __launch_bounds__(kBlock) g_dots3(const PcgArgs* ap, PcgRun* run
     run->ticket[SLOT_PKP] = 0;
   }
 }
+// column-split layout: r'y (a sum) and ||r||_inf (a maximum) of the ranks travel in ONE sum
+// all-reduce: every rank writes its pair into its own slot of a zeroed array ...
+__global__ void g_slots_put(PcgRun* run, int rank, int world) {
+  if (threadIdx.x || blockIdx.x) return;
+  for (int r = 0; r < world; r++) {
+    run->slots[2 * r]     = (r == rank) ? run->rTy : 0.0;
+    run->slots[2 * r + 1] = (r == rank) ? run->rnorm : 0.0;
+  }
+}
+// ... and folds the gathered pairs in rank order afterwards (identical on every rank)
+__global__ void g_slots_fold(PcgRun* run, int world) {
+  if (threadIdx.x || blockIdx.x) return;
+  double s = 0.0, mx = 0.0;
+  for (int r = 0; r < world; r++) {
+    s += run->slots[2 * r];
+    mx = fmax(mx, run->slots[2 * r + 1]);
+  }
+  run->rTy = s;
+  run->rnorm = mx;
+}
 // alpha, beta from the (exchanged) dots
 __global__ void g_step_scalars(PcgRun* run) {
   if (threadIdx.x || blockIdx.x) return;
@@ -868,6 +888,21 @@ inline void exchange_vector(T* d_v, int n) {
 inline void exchange_scalars(double* d_first, int count, bool is_max) {
   if (dist_split()) dist_allreduce_f64(d_first, count, is_max);
 }
+// (r'y, ||r||_inf): one collective for the pair
+inline void exchange_residual_scalars(PcgRun* run, cudaStream_t st) {
+  if (!dist_split()) return;
+  const int world = b200_dist_world(), rank = b200_dist_rank();
+  if (world > 8) {       // slots[] holds 8 ranks; beyond that fall back to two collectives
+    dist_allreduce_f64(&run->rTy, 1, false);
+    dist_allreduce_f64(&run->rnorm, 1, true);
+    return;
+  }
+  g_slots_put<<<1, 32, 0, st>>>(run, rank, world);
+  count_launch("g_slots_put");
+  dist_allreduce_f64(run->slots, 2 * world, false);
+  g_slots_fold<<<1, 32, 0, st>>>(run, world);
+  count_launch("g_slots_fold");
+}
 }  // namespace
 
 int b200_pcg_sharded_solve(b200_pcg* s, const PcgArgs& a) {
@@ -886,31 +921,30 @@ int b200_pcg_sharded_solve(b200_pcg* s, const PcgArgs& a) {
   if (a.polishing || a.admm_iter == 1) {
     if (m > 0) {
       g_rhs_t<<<ew_grid(m), kBlock, 0, st>>>(d_args);
-      count_launch();
+      count_launch("g_rhs_t");
       g_pass_At<<<pass_grid(*s->At, cap), kSpmvBlock, kSpmvSmemBytes, st>>>(d_args);
-      count_launch();
+      count_launch("g_rhs_t");
     } else {
       B200_CHECK(cudaMemsetAsync(s->d_Kp, 0, sizeof(T) * n, st));
     }
     exchange_vector(s->d_Kp, n);
     g_rhs_norm_sum<<<gn, kBlock, 0, st>>>(d_args, run, s->d_gred, cap, 1, off);
-    count_launch();
+    count_launch("g_rhs_norm_sum");
     exchange_scalars(&run->rhs_norm, 1, true);
   }
   g_tolerance<<<1, 32, 0, st>>>(d_args, run);
-  count_launch();
+  count_launch("g_tolerance");
   if (m > 0) {
     if (a.ax_valid) g_p1_carried<<<ew_grid(m), kBlock, 0, st>>>(d_args);
     else g_pass_A<0><<<pass_grid(*s->A, cap), kSpmvBlock, kSpmvSmemBytes, st>>>(d_args);
-    count_launch();
+    count_launch("g_p1_carried");
   }
   g_pass_K<2><<<pass_grid(s->K2, cap), kSpmvBlock, kSpmvSmemBytes, st>>>(d_args, run, s->d_gred, cap);
-  count_launch();
+  count_launch("g_p1_carried");
   exchange_vector(s->d_Kp, n);
   g_resid_init<<<gn, kBlock, 0, st>>>(d_args, run, s->d_gred, cap, off);
-  count_launch();
-  exchange_scalars(&run->rTy, 1, false);
-  exchange_scalars(&run->rnorm, 1, true);
+  count_launch("g_resid_init");
+  exchange_residual_scalars(run, st);
 
   PcgRun h;
   bool ok = true;
@@ -919,26 +953,26 @@ int b200_pcg_sharded_solve(b200_pcg* s, const PcgArgs& a) {
   for (;;) {
     ok &= B200_CHECK(cudaMemcpyAsync(&h, run, sizeof(PcgRun), cudaMemcpyDeviceToHost, st));
     ok &= B200_CHECK(cudaStreamSynchronize(st));
+    if (ctx().trace_on) trace_point("host read of the loop condition");
     if (!ok || !(h.rnorm > h.eps && h.it < a.max_iter)) break;
     if (m > 0) {
       g_pass_A<1><<<pass_grid(*s->A, cap), kSpmvBlock, kSpmvSmemBytes, st>>>(d_args);
-      count_launch();
+      count_launch("g_resid_init");
     }
     g_pass_K<3><<<pass_grid(s->K2, cap), kSpmvBlock, kSpmvSmemBytes, st>>>(d_args, run, s->d_gred, cap);
-    count_launch();
+    count_launch("g_resid_init");
     exchange_vector(s->d_Kp, n);
     g_dots3<<<gn, kBlock, 0, st>>>(d_args, run, s->d_gred, cap, off);
-    count_launch();
+    count_launch("g_dots3");
     exchange_scalars(run->dots, 3, false);
     g_step_scalars<<<1, 32, 0, st>>>(run);
-    count_launch();
+    count_launch("g_step_scalars");
     g_update_fused<<<gu, kBlock, 0, st>>>(d_args, run, s->d_gred, cap, none, off);
-    count_launch();
-    exchange_scalars(&run->rTy, 1, false);
-    exchange_scalars(&run->rnorm, 1, true);
+    count_launch("g_update_fused");
+    exchange_residual_scalars(run, st);
   }
   g_epilogue<<<ew_grid(nm), kBlock, 0, st>>>(d_args, run);
-  count_launch();
+  count_launch("g_epilogue");
   return ok ? 0 : 1;
 }
 

@@ -91,8 +91,10 @@ def plan_column_split(P, A, world, max_link_degree=3):
     else:
         comp = np.arange(m)
     # label every cluster by its first row so that clusters keep the original row order
-    first = np.full(comp.max() + 1, m, dtype=np.int64)
-    np.minimum.at(first, comp, np.arange(m))
+    o = np.argsort(comp, kind="stable")                     # stable: the first row of a cluster comes first
+    starts_c = np.concatenate([[0], np.nonzero(np.diff(comp[o]))[0] + 1])
+    first = np.empty(comp.max() + 1, dtype=np.int64)
+    first[comp[o[starts_c]]] = o[starts_c]
     root = first[comp]
     # 2. clusters -> ranks, greedy in order of first row, balanced by nonzeros (+1 per row)
     Acsr = A.tocsr()
@@ -110,12 +112,13 @@ def plan_column_split(P, A, world, max_link_degree=3):
     rank_of_row[order] = cl_rank
     # 3. classify columns
     owner = np.full(n, -1, dtype=np.int64)
-    col_of_entry = np.repeat(np.arange(n), deg)
     r_entry = rank_of_row[A.indices]
     lo = np.full(n, world, dtype=np.int64)
     hi = np.full(n, -1, dtype=np.int64)
-    np.minimum.at(lo, col_of_entry, r_entry)
-    np.maximum.at(hi, col_of_entry, r_entry)
+    ne = np.nonzero(deg > 0)[0]                             # CSC: the entries of a column are contiguous
+    if ne.size:
+        lo[ne] = np.minimum.reduceat(r_entry, A.indptr[ne])
+        hi[ne] = np.maximum.reduceat(r_entry, A.indptr[ne])
     single = (deg > 0) & (lo == hi)
     owner[single] = lo[single]
     # columns coupled through P must live together: shared wins, propagate until stable

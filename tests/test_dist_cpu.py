@@ -80,3 +80,45 @@ def test_bench_reference_arm_other_ranks_exit_quietly():
     out = subprocess.run([sys.executable, str(ROOT / "bench.py"), "--impl", "reference", "--gpus", "2",
                           "--steps", "1", "--warmup", "1"], capture_output=True, text=True, env=env, timeout=120)
     assert out.returncode == 0 and out.stdout.strip() == ""
+
+
+@pytest.mark.parametrize("world", [2, 4])
+@pytest.mark.parametrize("family", ["lasso", "huber", "svm", "portfolio"])
+def test_column_split_plan_partitions_the_problem(family, world):
+    """Column-split layout: every row and every column has exactly one home, a rank's
+    rows touch only [shared ; its own] columns, P never couples columns of different ranks, and for
+    the epigraph families only the feature columns are shared."""
+    from osqp_b200.dist import plan_column_split, shard_problem_split
+    pb = {"lasso": lambda: problems.lasso(50, 500, density=0.05, seed=2),
+          "huber": lambda: problems.huber(20, 400, density=0.1),
+          "svm": lambda: problems.svm(20, 400, density=0.1),
+          "portfolio": lambda: problems.portfolio(300, 20, density=0.2)}[family]()
+    A = sp.csr_matrix(pb["A"])
+    P = sp.csc_matrix(pb["P"])
+    Pfull = (sp.triu(P) + sp.triu(P, 1).T).tocsr()
+    m, n = A.shape
+    plan = plan_column_split(P, A, world)
+    ns = plan["shared"].size
+    owned_cols, owned_rows = np.zeros(n, dtype=int), np.zeros(m, dtype=int)
+    owned_cols[plan["shared"]] += 1
+    nnzA = nnzP_local = 0
+    for r in range(world):
+        R, Cc = plan["rows"][r], plan["cols"][r]
+        assert np.array_equal(Cc[:ns], plan["shared"])
+        owned_rows[R] += 1
+        owned_cols[Cc[ns:]] += 1
+        sh = shard_problem_split(pb, r, plan)
+        assert sh["A"].shape[0] != sh["A"].shape[1]            # lengths tell row from column vectors
+        assert A[R].nnz == sh["A"].nnz                          # no entry of these rows lies outside Cc
+        nnzA += sh["A"].nnz
+        assert np.array_equal(sh["q"], np.asarray(pb["q"])[Cc])
+        # P restricted to this rank's columns keeps every coupling of its owned columns
+        own = Cc[ns:]
+        if own.size:
+            assert Pfull[own].nnz == Pfull[own][:, Cc].nnz
+            nnzP_local += Pfull[own][:, own].nnz
+    assert (owned_rows == 1).all() and (owned_cols == 1).all() and nnzA == A.nnz
+    if family != "portfolio":
+        assert ns <= 50 and ns < 0.2 * n
+    else:
+        assert ns == n                                          # no low-degree cut: falls back to row blocks

@@ -81,6 +81,17 @@ def summarise_trace(path, last_launches):
         print(f"    {tag:48s} n={cnt:5d}  dev {dev/1e3:8.2f} ms ({100*dev/tot:5.1f} %)  {dev/cnt:8.1f} us each   host {host/cnt:7.1f} us each")
 
 
+def summarise_marked(path):
+    """Rows between the last solve-begin / solve-end markers of a trace."""
+    lines = open(path).read().splitlines()[1:]
+    tags = [ln.split(",", 1)[1].rsplit(",", 2)[0] for ln in lines]
+    b = max(i for i, t in enumerate(tags) if t == "solve-begin")
+    e = max(i for i, t in enumerate(tags) if t == "solve-end")
+    tmp = path + ".last"
+    open(tmp, "w").write("hdr\n" + "\n".join(lines[b + 1:e]) + "\n")
+    summarise_trace(tmp, e - b - 1)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--child", action="store_true")
@@ -88,7 +99,10 @@ def main():
     ap.add_argument("--scale", type=float, default=1.0)
     ap.add_argument("--reps", type=int, default=3)
     ap.add_argument("--drivers", default="graph,persistent")
+    ap.add_argument("--summarise", default=None, help="trace CSV with solve-begin/solve-end markers")
     args = ap.parse_args()
+    if args.summarise:
+        return summarise_marked(args.summarise)
     if args.child:
         return child(args)
     os.makedirs("gpurun_out", exist_ok=True)

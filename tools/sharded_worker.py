@@ -21,6 +21,8 @@ ap.add_argument("--layout", default="split", choices=["split", "rows"])
 args = ap.parse_args()
 
 local = int(os.environ.get("LOCAL_RANK", "0"))
+if os.environ.get("B200_TRACE_FILE"):     # one launch trace per rank
+    os.environ["B200_TRACE_FILE"] += f".rank{os.environ.get('RANK', '0')}"
 torch.cuda.set_device(local)
 dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 rank, world = dist.get_rank(), dist.get_world_size()
@@ -48,7 +50,9 @@ t0 = time.perf_counter(); prob.setup(pb["P"], pb["q"], pb["A"], pb["l"], pb["u"]
 best = None
 for rep in range(args.reps):
     dist.barrier(); torch.cuda.synchronize()
+    k.b200_trace_mark(b"solve-begin")
     ta = time.perf_counter(); r = prob.solve(); tb = time.perf_counter()
+    k.b200_trace_mark(b"solve-end")
     tmax = torch.tensor([tb - ta], device="cuda", dtype=torch.float64); dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
     best = tmax.item() if best is None else min(best, tmax.item())
 cg, ns = prob.cg_stats()
@@ -88,4 +92,5 @@ if rank == 0:
 prob.cleanup()
 dist.barrier()
 k.b200_dist_finalize()
+k.b200_shutdown()
 dist.destroy_process_group()
