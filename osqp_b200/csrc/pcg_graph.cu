@@ -432,7 +432,8 @@ __global__ void g_step_scalars(PcgRun* run) {
 //   MODE 1: L2   Kp = [P + sigma I | A'] [p; t] ; totals p'Kp, r'M^-1 Kp, Kp'M^-1 Kp -> alpha, beta
 //   MODE 2: P2   r = K2 [x; t] - b1 ; p = -M^-1 r ; totals r'y, ||r||_inf
 //   MODE 3: P1   Ax = A x ; t = rho .* (Ax - b2)       (exact recomputation of the carried product)
-//   MODE 4/5: phase profile only (plain A' t, plain K2 [p; t])
+//   MODE 4: Kp = A' t   MODE 5: Kp = K2 [p; t]   MODE 6: Kp = K2 [x; t]   (plain stores: the row-sharded
+//           driver exchanges the partial Kp before any scalar is formed; also the phase profile)
 constexpr int kLeanBlock = 512;
 constexpr int kLeanCtasPerSm = 3;
 static_assert(kTile == 4 * kLeanBlock, "lean pass assumes one batch of 4 per thread");
@@ -452,7 +453,7 @@ __global__ void __launch_bounds__(kLeanBlock, kLeanCtasPerSm) g_lean_pass(const 
   const T* __restrict__   val     = M.val;
   const int4* __restrict__ desc   = M.desc;
   const int nblocks = M.nblocks;
-  const T* __restrict__ src = (MODE == 4) ? a.t : ((MODE == 0 || MODE == 1 || MODE == 5) ? a.p : a.x);
+  const T* __restrict__ src = (MODE == 4) ? a.t : ((MODE == 0 || MODE == 1 || MODE == 5) ? a.p : a.x);   // 2, 3, 6: x
   const T* __restrict__ t = a.t;
   const int n = a.n;
   const int tid = threadIdx.x;
@@ -706,6 +707,23 @@ int b200_pcg_graph_build(b200_pcg* s) {
   ok &= B200_CHECK(dev_malloc(&s->d_gred, sizeof(double) * SLOT_COUNT * s->gred_stride));
   if (!ok) return 1;
   B200_CHECK(cudaMemsetAsync(s->d_run, 0, sizeof(PcgRun), c.stream));
+  // lean flat kernels when neither matrix has over-long rows (checked on the host schedules)
+  bool lean = getenv("B200_PCG_NO_LEAN") == nullptr;
+  if (lean) {
+    auto fetch = [&](const b200_csr& M) {
+      std::vector<int4> h(M.nblocks > 0 ? M.nblocks : 0);
+      if (M.nblocks > 0) {
+        B200_CHECK(cudaMemcpyAsync(h.data(), M.d_desc, sizeof(int4) * M.nblocks, cudaMemcpyDeviceToHost, c.stream));
+        B200_CHECK(cudaStreamSynchronize(c.stream));
+      }
+      return h;
+    };
+    lean = lean_ok(s->K2, fetch(s->K2)) && (s->m == 0 || lean_ok(*s->A, fetch(*s->A)));
+  }
+  s->lean = lean ? 1 : 0;
+  if (getenv("B200_TRACE_SETUP"))
+    fprintf(stderr, "[b200 trace] graph PCG driver: %s passes, K2 tiles %d, A tiles %d, partial stride %d\n",
+            lean ? "lean" : "generic", s->K2.nblocks, s->m > 0 ? s->A->nblocks : 0, s->gred_stride);
   if (s->sharded) return 0;   // host-driven loop with an all-reduce per iteration: no graph
 
   cudaGraph_t g = nullptr;
@@ -749,24 +767,6 @@ int b200_pcg_graph_build(b200_pcg* s) {
     prev = node;
   };
   const int cap = s->gred_stride;
-  // lean flat kernels when neither matrix has over-long rows (checked on the host schedules)
-  bool lean = getenv("B200_PCG_NO_LEAN") == nullptr;
-  if (lean) {
-    auto fetch = [&](const b200_csr& M) {
-      std::vector<int4> h(M.nblocks > 0 ? M.nblocks : 0);
-      if (M.nblocks > 0) {
-        B200_CHECK(cudaMemcpyAsync(h.data(), M.d_desc, sizeof(int4) * M.nblocks, cudaMemcpyDeviceToHost, c.stream));
-        B200_CHECK(cudaStreamSynchronize(c.stream));
-      }
-      return h;
-    };
-    lean = lean_ok(s->K2, fetch(s->K2)) && (s->m == 0 || lean_ok(*s->A, fetch(*s->A))) &&
-           s->K2.nblocks <= cap && (s->m == 0 || s->A->nblocks <= cap);
-  }
-  s->lean = lean ? 1 : 0;
-  if (getenv("B200_TRACE_SETUP"))
-    fprintf(stderr, "[b200 trace] graph PCG driver: %s passes, K2 tiles %d, A tiles %d, partial stride %d\n",
-            lean ? "lean" : "generic", s->K2.nblocks, s->m > 0 ? s->A->nblocks : 0, cap);
   if (s->m > 0) {
     if (lean) {
       void* a1[] = {(void*)&d_args, (void*)&d_run, (void*)&d_red, (void*)&stride};
@@ -936,10 +936,12 @@ int b200_pcg_sharded_solve(b200_pcg* s, const PcgArgs& a) {
   count_launch("g_tolerance");
   if (m > 0) {
     if (a.ax_valid) g_p1_carried<<<ew_grid(m), kBlock, 0, st>>>(d_args);
+    else if (s->lean) g_lean_pass<3><<<lean_grid(*s->A, false), kLeanBlock, 0, st>>>(d_args, run, s->d_gred, cap);
     else g_pass_A<0><<<pass_grid(*s->A, cap), kSpmvBlock, kSpmvSmemBytes, st>>>(d_args);
     count_launch("g_p1_carried");
   }
-  g_pass_K<2><<<pass_grid(s->K2, cap), kSpmvBlock, kSpmvSmemBytes, st>>>(d_args, run, s->d_gred, cap);
+  if (s->lean) g_lean_pass<6><<<lean_grid(s->K2, false), kLeanBlock, 0, st>>>(d_args, run, s->d_gred, cap);
+  else g_pass_K<2><<<pass_grid(s->K2, cap), kSpmvBlock, kSpmvSmemBytes, st>>>(d_args, run, s->d_gred, cap);
   count_launch("g_p1_carried");
   exchange_vector(s->d_Kp, n);
   g_resid_init<<<gn, kBlock, 0, st>>>(d_args, run, s->d_gred, cap, off);
@@ -956,10 +958,12 @@ int b200_pcg_sharded_solve(b200_pcg* s, const PcgArgs& a) {
     if (ctx().trace_on) trace_point("host read of the loop condition");
     if (!ok || !(h.rnorm > h.eps && h.it < a.max_iter)) break;
     if (m > 0) {
-      g_pass_A<1><<<pass_grid(*s->A, cap), kSpmvBlock, kSpmvSmemBytes, st>>>(d_args);
+      if (s->lean) g_lean_pass<0><<<lean_grid(*s->A, false), kLeanBlock, 0, st>>>(d_args, run, s->d_gred, cap);
+      else g_pass_A<1><<<pass_grid(*s->A, cap), kSpmvBlock, kSpmvSmemBytes, st>>>(d_args);
       count_launch("g_resid_init");
     }
-    g_pass_K<3><<<pass_grid(s->K2, cap), kSpmvBlock, kSpmvSmemBytes, st>>>(d_args, run, s->d_gred, cap);
+    if (s->lean) g_lean_pass<5><<<lean_grid(s->K2, false), kLeanBlock, 0, st>>>(d_args, run, s->d_gred, cap);
+    else g_pass_K<3><<<pass_grid(s->K2, cap), kSpmvBlock, kSpmvSmemBytes, st>>>(d_args, run, s->d_gred, cap);
     count_launch("g_resid_init");
     exchange_vector(s->d_Kp, n);
     g_dots3<<<gn, kBlock, 0, st>>>(d_args, run, s->d_gred, cap, off);
