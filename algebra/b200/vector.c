@@ -262,7 +262,7 @@ OSQPInt b200_dist_nglobal = -1;
     }                                                                   \
   } while (0)
 
-static b200_norm_cache g_cache;
+static _Thread_local b200_norm_cache g_cache;   /* one per host thread, like the library context */
 
 void b200_norm_cache_reset(void) { g_cache.count = 0; g_cache.epoch = 0; }
 

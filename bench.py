@@ -18,6 +18,7 @@ N > 1  : the path shards as independent QPs (BASELINE configs[4] style): every r
          restatement = oracle/_ref/libosqp_builtin.so) on a bounded sample of the same generator.
 """
 import argparse
+import ctypes
 import json
 import os
 import subprocess
@@ -299,6 +300,8 @@ def run_b200(args):
     sampler = ClockSampler(local) if rank == 0 else None
     barrier()
     l0 = k.b200_launch_count()
+    k.b200_graph_launch_count.restype = ctypes.c_ulonglong
+    g0 = k.b200_graph_launch_count()
     k.b200_event_record(e0)
     iters = 0
     for _ in range(args.steps):
@@ -310,6 +313,11 @@ def run_b200(args):
     barrier()
     clocks = sampler.stop() if sampler else None
     cg1, ns1 = solver.cg_stats()
+    # a graph launch is one enqueue but 1 + 3 k kernels (loop-init node, then A pass / operator
+    # pass / fused update per CG iteration): count the kernels, not the enqueues
+    k.b200_graph_launch_count.restype = ctypes.c_ulonglong
+    if k.b200_graph_launch_count() - g0 > 0:
+        launches += 3 * (cg1 - cg0)
     status, obj = r.info.status, r.info.obj_val
     solver.cleanup()
 

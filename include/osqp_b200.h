@@ -47,6 +47,9 @@ void b200_sync(void);                    /* wait for the library stream         
 void* b200_stream_handle(void);          /* cudaStream_t of the library stream      */
 int  b200_last_error(void);              /* sticky CUDA error code, 0 if none       */
 unsigned long long b200_launch_count(void); /* kernels launched since b200_init      */
+/* CUDA-graph launches of the PCG loop since b200_init: each is counted once by b200_launch_count
+ * but runs 1 + 3 k kernels (k = CG iterations of that solve, see b200_pcg_stats) */
+unsigned long long b200_graph_launch_count(void);
 /* launch tracer (development aid): with B200_TRACE_FILE set, every launch / collective records a
  * CUDA event + host time, dumped as CSV at b200_shutdown; this adds a named marker */
 void b200_trace_mark(const char* tag);

@@ -15,6 +15,7 @@ namespace b200 {
 constexpr int kBlock        = 256;    // threads per CTA for every kernel in the library
 constexpr int kMaxRedBlocks = 1184;   // 148 SMs x 8 CTAs: upper bound for reduction grids
 constexpr int kScalarSlots  = 32;
+constexpr int kMaxContexts  = 64;     // library contexts (= host threads with live solvers) per process
 constexpr int kMailSlots    = 32;     // result values; the sequence word lives at index kMailSlots
 
 struct Context {
@@ -37,11 +38,16 @@ struct Context {
   // staging buffer for host->device index/value uploads is allocated on demand
   int          last_error = 0;
   unsigned long long launches = 0;
+  unsigned long long graph_launches = 0;   // cudaGraphLaunch calls (each = 1 + 3 k kernels, k CG iterations)
   unsigned long long epoch    = 0;   // launches + device copies: anything that may change a vector
   char         name[256]  = {0};
   int          trace_on   = 0;   // B200_TRACE_FILE: one CUDA event + host timestamp per launch
+  int          slot       = 0;   // index of this context (per-context __constant__ argument blocks)
 };
 
+// ONE CONTEXT PER HOST THREAD (thread_local): its own stream, reduction workspace and result
+// mailbox.  A solver must be used from the thread that created it; solvers of different threads run
+// concurrently on the device (batches of small independent QPs: BASELINE configs[4]).
 Context& ctx();
 
 inline bool check(cudaError_t e, const char* what) {

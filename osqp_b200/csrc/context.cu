@@ -8,12 +8,29 @@
 #include <cstdlib>
 #include <ctime>
 #include <vector>
+#include <atomic>
 
 namespace b200 {
 Context& ctx() {
-  static Context c;
+  static thread_local Context c;
   return c;
 }
+
+namespace {
+static_assert(kMaxContexts <= 64, "slot mask is one 64-bit word");
+std::atomic<unsigned long long> g_slot_mask{0};
+int slot_acquire() {
+  for (;;) {
+    unsigned long long cur = g_slot_mask.load();
+    int free_bit = -1;
+    for (int i = 0; i < kMaxContexts; i++)
+      if (!(cur & (1ull << i))) { free_bit = i; break; }
+    if (free_bit < 0) return -1;
+    if (g_slot_mask.compare_exchange_weak(cur, cur | (1ull << free_bit))) return free_bit;
+  }
+}
+void slot_release(int i) { g_slot_mask.fetch_and(~(1ull << i)); }
+}  // namespace
 
 // ---- launch tracer: after every launch an event is recorded on the library stream together
 // with the host time of the call.  The dump lists, per launch, the device time since the previous
@@ -21,7 +38,7 @@ Context& ctx() {
 // is what separates "the GPU was busy" from "the GPU waited for the host".
 namespace {
 struct TracePoint { cudaEvent_t ev; const char* tag; double host_us; };
-std::vector<TracePoint> g_trace;
+thread_local std::vector<TracePoint> g_trace;
 double host_now_us() {
   timespec ts;
   clock_gettime(CLOCK_MONOTONIC, &ts);
@@ -59,8 +76,11 @@ void trace_point(const char* tag) {
   g_trace.push_back(t);
 }
 static void trace_dump() {
-  const char* path = getenv("B200_TRACE_FILE");
-  if (!path || g_trace.empty()) return;
+  const char* base = getenv("B200_TRACE_FILE");
+  if (!base || g_trace.empty()) return;
+  char path[1024];
+  if (ctx().slot > 0) snprintf(path, sizeof(path), "%s.ctx%d", base, ctx().slot);
+  else snprintf(path, sizeof(path), "%s", base);
   cudaStreamSynchronize(ctx().stream);
   FILE* f = fopen(path, "w");
   if (f) {
@@ -98,6 +118,11 @@ int b200_init(int device) {
   }
   if (device < 0 || device >= count) device = 0;
   if (!B200_CHECK(cudaSetDevice(device))) return 1;
+  c.slot = slot_acquire();
+  if (c.slot < 0) {
+    fprintf(stderr, "[osqp_b200] more than %d library contexts (host threads with live solvers)\n", kMaxContexts);
+    return 1;
+  }
   cudaDeviceProp prop;
   if (!B200_CHECK(cudaGetDeviceProperties(&prop, device))) return 1;
   c.device   = device;
@@ -147,6 +172,7 @@ void b200_shutdown(void) {
   cudaFreeHost(c.h_mail);
   c.h_mail = c.d_mail = nullptr;
   cudaStreamDestroy(c.stream);
+  slot_release(c.slot);
   c.d_partials = nullptr;
   c.d_ticket   = nullptr;
   c.d_scalar   = nullptr;
@@ -172,6 +198,8 @@ int b200_last_error(void) { return ctx().last_error; }
 unsigned long long b200_launch_count(void) { return ctx().launches; }
 
 unsigned long long b200_epoch(void) { return ctx().epoch; }
+
+unsigned long long b200_graph_launch_count(void) { return ctx().graph_launches; }
 
 void b200_trace_mark(const char* tag) {
   if (ctx().trace_on) trace_point(strdup(tag ? tag : "mark"));   // tags live until the dump

@@ -117,12 +117,13 @@ __device__ __forceinline__ bool publish_fold(const double* part, const int* slot
 // (the graph's kernel nodes have frozen parameters) reads pointers and scalars as constant-bank
 // operands -- no registers, no L1 traffic.  (Reading them through a pointer to global memory cost
 // one extra L1 wavefront per use in the per-row epilogues: 17 us of a 70 us pass.)
-__constant__ PcgArgs c_args;
+__constant__ PcgArgs c_args[kMaxContexts];   // one block per library context (host thread)
 
 inline bool set_args(const PcgArgs& a, cudaStream_t st) {
   // pageable source: the runtime stages the 300 bytes before returning; stream-ordered with the
   // kernels of the previous solve
-  return B200_CHECK(cudaMemcpyToSymbolAsync(c_args, &a, sizeof(PcgArgs), 0, cudaMemcpyHostToDevice, st));
+  return B200_CHECK(cudaMemcpyToSymbolAsync(c_args, &a, sizeof(PcgArgs), sizeof(PcgArgs) * (size_t)ctx().slot,
+                                            cudaMemcpyHostToDevice, st));
 }
 
 // step length and (predicted) direction coefficient of one CG iteration, from the three dots of
@@ -140,8 +141,8 @@ __device__ __forceinline__ void cg_step_scalars(PcgRun* run, double pKp, double 
 }
 
 // t = rho .* b2   (only for the ||rhs|| of the tolerance at admm_iter == 1 / polishing)
-__global__ void __launch_bounds__(kBlock) g_rhs_t(const PcgArgs* ap) {
-  const PcgArgs& a = c_args;
+__global__ void __launch_bounds__(kBlock) g_rhs_t(int slot) {
+  const PcgArgs& a = c_args[slot];
   const T* b2 = a.b + a.n;
   const int stride = gridDim.x * blockDim.x;
   for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < a.m; j += stride)
@@ -149,11 +150,11 @@ __global__ void __launch_bounds__(kBlock) g_rhs_t(const PcgArgs* ap) {
 }
 
 // ||b1 + A' t||_inf  -> run->rhs_norm
-__global__ void __launch_bounds__(kSpmvBlock, B200_SPMV_MINBLOCKS) g_rhs_norm(const PcgArgs* ap, PcgRun* run, double* red,
+__global__ void __launch_bounds__(kSpmvBlock, B200_SPMV_MINBLOCKS) g_rhs_norm(int slot, PcgRun* run, double* red,
                                                          int stride) {
   extern __shared__ __align__(128) unsigned char dsm[];
   __shared__ double shr[33];
-  const PcgArgs& a = c_args;
+  const PcgArgs& a = c_args[slot];
   Pipe pipe = pipe_init(dsm);
   const T* b1 = a.b;
   const T* t = a.t;
@@ -176,8 +177,8 @@ __global__ void __launch_bounds__(kSpmvBlock, B200_SPMV_MINBLOCKS) g_rhs_norm(co
 }
 
 // tolerance schedule of compute_tolerance (cuda_pcg_interface.cu:32-64), evaluated on the device
-__device__ __forceinline__ void tolerance_step(PcgRun* run) {
-  const PcgArgs& a = c_args;
+__device__ __forceinline__ void tolerance_step(PcgRun* run, int slot) {
+  const PcgArgs& a = c_args[slot];
   const PcgState st = *a.st;
   double rf = st.reduction_factor, eps_prev = st.eps_prev, eps;
   int zero_iters = st.zero_iters;
@@ -199,14 +200,14 @@ __device__ __forceinline__ void tolerance_step(PcgRun* run) {
   run->eps = eps; run->rf = rf; run->eps_prev = eps_prev; run->zero_iters = zero_iters;
   run->it = 0;
 }
-__global__ void g_tolerance(const PcgArgs* ap, PcgRun* run) {
+__global__ void g_tolerance(int slot, PcgRun* run) {
   if (threadIdx.x || blockIdx.x) return;
-  tolerance_step(run);
+  tolerance_step(run, slot);
 }
 
 // P1 from the carried product: t = rho .* (Ax - b2)
-__global__ void __launch_bounds__(kBlock) g_p1_carried(const PcgArgs* ap) {
-  const PcgArgs& a = c_args;
+__global__ void __launch_bounds__(kBlock) g_p1_carried(int slot) {
+  const PcgArgs& a = c_args[slot];
   const T* b2 = a.b + a.n;
   const int stride = gridDim.x * blockDim.x;
   for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < a.m; j += stride)
@@ -216,9 +217,9 @@ __global__ void __launch_bounds__(kBlock) g_p1_carried(const PcgArgs* ap) {
 // pass over A.  MODE 0: P1 with exact recomputation (Ax = A x ; t = rho .* (Ax - b2))
 //               MODE 1: L1 (w = A p ; t = rho .* w)
 template <int MODE>
-__global__ void __launch_bounds__(kSpmvBlock, B200_SPMV_MINBLOCKS) g_pass_A(const PcgArgs* ap) {
+__global__ void __launch_bounds__(kSpmvBlock, B200_SPMV_MINBLOCKS) g_pass_A(int slot) {
   extern __shared__ __align__(128) unsigned char dsm[];
-  const PcgArgs& a = c_args;
+  const PcgArgs& a = c_args[slot];
   Pipe pipe = pipe_init(dsm);
   const T* src = (MODE == 0) ? a.x : a.p;
   const T* b2 = a.b + a.n;
@@ -242,11 +243,11 @@ __global__ void __launch_bounds__(kSpmvBlock, B200_SPMV_MINBLOCKS) g_pass_A(cons
 //   MODE 2/3 (row-sharded): Kp = this rank's PARTIAL K2 [x; t] / K2 [p; t]; the all-reduce and
 //           the scalars follow in separate kernels (g_resid_init / g_dot_pKp)
 template <int MODE>
-__global__ void __launch_bounds__(kSpmvBlock, B200_SPMV_MINBLOCKS) g_pass_K(const PcgArgs* ap, PcgRun* run, double* red,
+__global__ void __launch_bounds__(kSpmvBlock, B200_SPMV_MINBLOCKS) g_pass_K(int slot, PcgRun* run, double* red,
                                                        int stride) {
   extern __shared__ __align__(128) unsigned char dsm[];
   __shared__ double shr[33];
-  const PcgArgs& a = c_args;
+  const PcgArgs& a = c_args[slot];
   Pipe pipe = pipe_init(dsm);
   const int n = a.n;
   const T* src = (MODE == 0 || MODE == 2) ? a.x : a.p;
@@ -310,9 +311,9 @@ __global__ void __launch_bounds__(kSpmvBlock, B200_SPMV_MINBLOCKS) g_pass_K(cons
 }
 
 // row-sharded: Kp[i] = (A_r' t)_i partial, for the ||rhs|| of the tolerance
-__global__ void __launch_bounds__(kSpmvBlock, B200_SPMV_MINBLOCKS) g_pass_At(const PcgArgs* ap) {
+__global__ void __launch_bounds__(kSpmvBlock, B200_SPMV_MINBLOCKS) g_pass_At(int slot) {
   extern __shared__ __align__(128) unsigned char dsm[];
-  const PcgArgs& a = c_args;
+  const PcgArgs& a = c_args[slot];
   Pipe pipe = pipe_init(dsm);
   const T* t = a.t;
   T* Kp = a.Kp;
@@ -323,10 +324,10 @@ __global__ void __launch_bounds__(kSpmvBlock, B200_SPMV_MINBLOCKS) g_pass_At(con
 }
 
 // row-sharded: ||b1 + Kp||_inf -> run->rhs_norm   (Kp = all-reduced A'(rho .* b2))
-__global__ void __launch_bounds__(kBlock) g_rhs_norm_sum(const PcgArgs* ap, PcgRun* run, double* red,
+__global__ void __launch_bounds__(kBlock) g_rhs_norm_sum(int slot, PcgRun* run, double* red,
                                                          int stride, int have_At, int off) {
   __shared__ double shr[33];
-  const PcgArgs& a = c_args;
+  const PcgArgs& a = c_args[slot];
   double mx = 0.0;
   for (int i = off + blockIdx.x * blockDim.x + threadIdx.x; i < a.n; i += gridDim.x * blockDim.x)
     mx = fmax(mx, fabs((double)(a.b[i] + (have_At ? a.Kp[i] : (T)0))));
@@ -340,10 +341,10 @@ __global__ void __launch_bounds__(kBlock) g_rhs_norm_sum(const PcgArgs* ap, PcgR
 
 // row-sharded P2 tail: r = Kp - b1 ; p = -M^-1 r ; totals r'y, ||r||_inf (n-vectors are replicated,
 // so every rank computes the same totals and no scalar exchange is needed)
-__global__ void __launch_bounds__(kBlock) g_resid_init(const PcgArgs* ap, PcgRun* run, double* red,
+__global__ void __launch_bounds__(kBlock) g_resid_init(int slot, PcgRun* run, double* red,
                                                        int stride, int off) {
   __shared__ double shr[33];
-  const PcgArgs& a = c_args;
+  const PcgArgs& a = c_args[slot];
   double acc0 = 0.0, acc1 = 0.0;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < a.n; i += gridDim.x * blockDim.x) {
     const T rr = a.Kp[i] - a.b[i];
@@ -371,9 +372,9 @@ __global__ void __launch_bounds__(kBlock) g_resid_init(const PcgArgs* ap, PcgRun
 
 // row-sharded L2 tail: the three dots of the exchanged Kp (p'Kp, r'M^-1 Kp, Kp'M^-1 Kp) over the
 // columns this rank counts; summed over the ranks afterwards when the layout is column-split
-__global__ void __launch_bounds__(kBlock) g_dots3(const PcgArgs* ap, PcgRun* run, double* red, int stride, int off) {
+__global__ void __launch_bounds__(kBlock) g_dots3(int slot, PcgRun* run, double* red, int stride, int off) {
   __shared__ double shr[48];
-  const PcgArgs& a = c_args;
+  const PcgArgs& a = c_args[slot];
   double acc = 0.0, acc1 = 0.0, acc2 = 0.0;
   for (int i = off + blockIdx.x * blockDim.x + threadIdx.x; i < a.n; i += gridDim.x * blockDim.x) {
     const T kp = a.Kp[i];
@@ -439,12 +440,12 @@ constexpr int kLeanCtasPerSm = 3;
 static_assert(kTile == 4 * kLeanBlock, "lean pass assumes one batch of 4 per thread");
 
 template <int MODE>
-__global__ void __launch_bounds__(kLeanBlock, kLeanCtasPerSm) g_lean_pass(const PcgArgs* ap, PcgRun* run, double* red,
+__global__ void __launch_bounds__(kLeanBlock, kLeanCtasPerSm) g_lean_pass(int slot, PcgRun* run, double* red,
                                                                           int stride) {
   __shared__ T sm[kTile];
   __shared__ int srp[kMaxRows + 1];
   __shared__ double shr[48];
-  const PcgArgs& a = c_args;
+  const PcgArgs& a = c_args[slot];
   // everything the tiles need is pulled out of the (global-memory) argument block once
   constexpr bool kOverA = (MODE == 0 || MODE == 3 || MODE == 4);
   const CsrView& M = (MODE == 4) ? a.At : (kOverA ? a.A : a.K2);
@@ -560,17 +561,17 @@ static bool lean_ok(const b200_csr& M, const std::vector<int4>& desc) {
 }
 
 // first node of the loop graph: arm the WHILE condition from the initial residual
-__global__ void g_loop_init(const PcgArgs* ap, PcgRun* run, cudaGraphConditionalHandle h) {
+__global__ void g_loop_init(int slot, PcgRun* run, cudaGraphConditionalHandle h) {
   if (threadIdx.x || blockIdx.x) return;
-  tolerance_step(run);      // the schedule only needs ||rhs|| (first solve / polish), known by now
-  cudaGraphSetConditional(h, (run->rnorm > run->eps && run->it < c_args.max_iter) ? 1u : 0u);
+  tolerance_step(run, slot);      // the schedule only needs ||rhs|| (first solve / polish), known by now
+  cudaGraphSetConditional(h, (run->rnorm > run->eps && run->it < c_args[slot].max_iter) ? 1u : 0u);
 }
 
 // L3: x += a p ; r += a Kp ; Ax += a w ; totals r'y, ||r||_inf ; last CTA: beta, it++, condition
-__global__ void __launch_bounds__(kBlock) g_update(const PcgArgs* ap, PcgRun* run, double* red, int stride,
+__global__ void __launch_bounds__(kBlock) g_update(int slot, PcgRun* run, double* red, int stride,
                                                    cudaGraphConditionalHandle h) {
   __shared__ double shr[33];
-  const PcgArgs& a = c_args;
+  const PcgArgs& a = c_args[slot];
   const int n = a.n, m = a.m;
   const T alpha = (T)(run->rTy / run->pKp);
   const int gtid = blockIdx.x * blockDim.x + threadIdx.x, gstride = gridDim.x * blockDim.x;
@@ -602,8 +603,8 @@ __global__ void __launch_bounds__(kBlock) g_update(const PcgArgs* ap, PcgRun* ru
 }
 
 // L4: p = beta p - M^-1 r
-__global__ void __launch_bounds__(kBlock) g_direction(const PcgArgs* ap, const PcgRun* run) {
-  const PcgArgs& a = c_args;
+__global__ void __launch_bounds__(kBlock) g_direction(int slot, const PcgRun* run) {
+  const PcgArgs& a = c_args[slot];
   const T beta = (T)run->beta;
   const int stride = gridDim.x * blockDim.x;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < a.n; i += stride)
@@ -612,10 +613,10 @@ __global__ void __launch_bounds__(kBlock) g_direction(const PcgArgs* ap, const P
 
 // L3+L4 in one kernel (graph driver): x += a p ; r += a Kp ; p = beta p - M^-1 r ; Ax += a w ;
 // totals r'y (exact), ||r||_inf ; last CTA: it++, loop condition.  8 n F + 3 m F bytes.
-__global__ void __launch_bounds__(kBlock) g_update_fused(const PcgArgs* ap, PcgRun* run, double* red, int stride,
+__global__ void __launch_bounds__(kBlock) g_update_fused(int slot, PcgRun* run, double* red, int stride,
                                                          cudaGraphConditionalHandle h, int off) {
   __shared__ double shr[33];
-  const PcgArgs& a = c_args;
+  const PcgArgs& a = c_args[slot];
   const int n = a.n, m = a.m;
   const T alpha = (T)run->alpha, beta = (T)run->beta;
   T* __restrict__ x = a.x; T* __restrict__ p = a.p; T* __restrict__ r = a.r;
@@ -653,8 +654,8 @@ __global__ void __launch_bounds__(kBlock) g_update_fused(const PcgArgs* ap, PcgR
 }
 
 // E1: b1 = x ; b2 = A x (carried) or (A x - b2)/delta when polishing ; persist the schedule state
-__global__ void __launch_bounds__(kBlock) g_epilogue(const PcgArgs* ap, PcgRun* run) {
-  const PcgArgs& a = c_args;
+__global__ void __launch_bounds__(kBlock) g_epilogue(int slot, PcgRun* run) {
+  const PcgArgs& a = c_args[slot];
   T* b1 = a.b;
   T* b2 = a.b + a.n;
   const int gtid = blockIdx.x * blockDim.x + threadIdx.x, gstride = gridDim.x * blockDim.x;
@@ -731,7 +732,7 @@ int b200_pcg_graph_build(b200_pcg* s) {
   cudaGraphConditionalHandle h;
   if (!B200_CHECK(cudaGraphConditionalHandleCreate(&h, g, 0, cudaGraphCondAssignDefault))) return 1;
 
-  const PcgArgs* d_args = s->d_args;
+  const int d_args = ctx().slot;
   PcgRun* d_run = s->d_run;
   double* d_red = s->d_gred;
   int stride = s->gred_stride;
@@ -814,7 +815,7 @@ int b200_pcg_graph_solve(b200_pcg* s, const PcgArgs& a) {
   const int n = s->n, m = s->m;
   set_args(a, st);
   ctx().epoch++;
-  const PcgArgs* d_args = s->d_args;
+  const int d_args = ctx().slot;
   if (a.polishing || a.admm_iter == 1) {
     if (m > 0) {
       g_rhs_t<<<ew_grid(m), kBlock, 0, st>>>(d_args);
@@ -862,6 +863,7 @@ int b200_pcg_graph_solve(b200_pcg* s, const PcgArgs& a) {
   } else {
     ok = B200_CHECK(cudaGraphLaunch((cudaGraphExec_t)s->graph_exec, st));
     count_launch("graph(loop)");
+    ctx().graph_launches++;
   }
   const int nm = n > m ? n : m;
   g_epilogue<<<ew_grid(nm), kBlock, 0, st>>>(d_args, s->d_run);
@@ -914,7 +916,7 @@ int b200_pcg_sharded_solve(b200_pcg* s, const PcgArgs& a) {
   const int off = dist_col_off();
   set_args(a, st);
   ctx().epoch++;
-  const PcgArgs* d_args = s->d_args;
+  const int d_args = ctx().slot;
   PcgRun* run = s->d_run;
   cudaGraphConditionalHandle none = 0;
 
@@ -985,7 +987,7 @@ int b200_pcg_sharded_solve(b200_pcg* s, const PcgArgs& a) {
 // launches, CUDA events on the library stream).  The iterate is left in an arbitrary state:
 // call it on a solver that is thrown away afterwards.
 namespace {
-b200_pcg* g_profile_target = nullptr;
+thread_local b200_pcg* g_profile_target = nullptr;
 __global__ void g_nop() {}
 }
 void b200_pcg_profile_register(b200_pcg* s, bool alive) {
@@ -999,7 +1001,7 @@ extern "C" int b200_pcg_profile_last(int reps, double* out_us, int nout) {
   Context& c = ctx();
   cudaStream_t st = c.stream;
   const int cap = s->gred_stride;
-  const PcgArgs* d_args = s->d_args;
+  const int d_args = ctx().slot;
   PcgRun* run = s->d_run;
   double* red = s->d_gred;
   const int n = s->n, m = s->m, nm = n > m ? n : m;
