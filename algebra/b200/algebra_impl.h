@@ -42,6 +42,7 @@ struct OSQPMatrix_ {
   OSQPInt   is_symmetric;
   OSQPInt*  h_map;    /* user CSC k -> position in S (A: CSR pos; P: upper copy) */
   OSQPInt*  h_map2;   /* P only: position of the mirrored copy, -1 on diagonal   */
+  OSQPInt*  d_map;    /* A built by the device transpose: the same map as h_map, in HBM (h_map NULL) */
 };
 
 /*

@@ -236,10 +236,10 @@ OSQPMatrix* OSQPMatrix_new_from_csc(const OSQPCscMatrix* M, OSQPInt is_triu) {
   out->n            = M->n;
   out->nnz_user     = nnz;
   out->is_symmetric = is_triu ? 1 : 0;
-  out->h_map        = (OSQPInt*)c_malloc(((size_t)nnz + 1) * sizeof(OSQPInt));
-  if (!out->h_map) goto fail;
 
   if (is_triu) {
+    out->h_map = (OSQPInt*)c_malloc(((size_t)nnz + 1) * sizeof(OSQPInt));
+    if (!out->h_map) goto fail;
     out->h_map2 = (OSQPInt*)c_malloc(((size_t)nnz + 1) * sizeof(OSQPInt));
     if (!out->h_map2) goto fail;
     out->S  = full_from_triu(M->n, M->p, M->i, M->x, out->h_map, out->h_map2);
@@ -250,8 +250,17 @@ OSQPMatrix* OSQPMatrix_new_from_csc(const OSQPCscMatrix* M, OSQPInt is_triu) {
     out->St = b200_csr_create((int)M->n, (int)M->m, (int)nnz, M->p, M->i, M->x);
     t1 = now_ms();
     if (trace_on()) fprintf(stderr, "[b200 trace] A: upload A' %.1f ms\n", t1 - t0);
-    out->S  = csr_from_csc(M->m, M->n, M->p, M->i, M->x, out->h_map);
-    if (!out->S || !out->St) goto fail;
+    if (!out->St) goto fail;
+    /* CSR(A): transposed on the device from the copy that is already there; the host counting
+       sort + second upload remain for matrices with over-long rows (and B200_HOST_TRANSPOSE=1) */
+    if (!getenv("B200_HOST_TRANSPOSE")) out->S = b200_csr_transpose(out->St, &out->d_map);
+    if (!out->S) {
+      out->d_map = OSQP_NULL;
+      out->h_map = (OSQPInt*)c_malloc(((size_t)nnz + 1) * sizeof(OSQPInt));
+      if (!out->h_map) goto fail;
+      out->S = csr_from_csc(M->m, M->n, M->p, M->i, M->x, out->h_map);
+    }
+    if (!out->S) goto fail;
   }
   if (trace_on()) { b200_sync(); fprintf(stderr, "[b200 trace] new_from_csc(%s) %.1f ms\n", is_triu ? "P" : "A", now_ms() - t0); }
   return out;
@@ -267,6 +276,7 @@ void OSQPMatrix_free(OSQPMatrix* M) {
     b200_csr_destroy(M->St);
     c_free(M->h_map);
     c_free(M->h_map2);
+    b200_free(M->d_map);
     c_free(M);
   }
 }
@@ -301,9 +311,27 @@ void OSQPMatrix_update_values(OSQPMatrix* M, const OSQPFloat* Mx_new, const OSQP
 
   d_x   = (OSQPFloat*)b200_malloc((size_t)cnt * sizeof(OSQPFloat));
   d_idx = (OSQPInt*)b200_malloc((size_t)cnt * sizeof(OSQPInt));
-  h_idx = (OSQPInt*)c_malloc((size_t)cnt * sizeof(OSQPInt));
-  if (!d_x || !d_idx || !h_idx) goto done;
+  if (!d_x || !d_idx) goto done;
   b200_copy_in(d_x, Mx_new, (size_t)cnt * sizeof(OSQPFloat));
+
+  if (M->d_map) {
+    /* A with a device-resident index map: positions are looked up in HBM */
+    if (!Mx_new_idx) {
+      b200_vec_scatter(b200_csr_values(M->S), d_x, M->d_map, (int)cnt);
+      b200_copy_in(b200_csr_values(M->St), d_x, (size_t)cnt * sizeof(OSQPFloat));
+    } else {
+      OSQPInt* d_pos = (OSQPInt*)b200_malloc((size_t)cnt * sizeof(OSQPInt));
+      if (!d_pos) goto done;
+      b200_copy_in(d_idx, Mx_new_idx, (size_t)cnt * sizeof(OSQPInt));
+      b200_veci_gather(d_pos, M->d_map, d_idx, (int)cnt);
+      b200_vec_scatter(b200_csr_values(M->S), d_x, d_pos, (int)cnt);
+      b200_vec_scatter(b200_csr_values(M->St), d_x, d_idx, (int)cnt);
+      b200_free(d_pos);
+    }
+    goto done;
+  }
+  h_idx = (OSQPInt*)c_malloc((size_t)cnt * sizeof(OSQPInt));
+  if (!h_idx) goto done;
 
   /* positions in S (for P: the upper copy) */
   for (k = 0; k < cnt; k++) h_idx[k] = M->h_map[Mx_new_idx ? Mx_new_idx[k] : k];

@@ -133,6 +133,15 @@ typedef struct b200_csr b200_csr;
 b200_csr* b200_csr_create(int nrows, int ncols, int nnz, const int* h_row_ptr,
                           const int* h_col_ind, const b200_float* h_val);
 void b200_csr_destroy(b200_csr* M);
+/* CSR of the transpose, built on the device from a matrix that is already there (count / scan /
+ * scatter / per-row rank sort: columns ascending inside every row, bit-identical to a host
+ * counting sort).  *d_map_out (optional) receives a device array of nnz ints: position in the
+ * result of every stored entry of Mt; free it with b200_free.  NULL when the result would have a row
+ * longer than 4096 entries (the caller keeps its host path) or on failure.
+ * replaces csr_transpose (algebra/cuda/src/cuda_csr.cu:489-560: thrust sort + cusparseCsr2cscEx2) */
+b200_csr* b200_csr_transpose(const b200_csr* Mt, int** d_map_out);
+void b200_veci_gather(int* d_dst, const int* d_src, const int* d_idx, int n);
+
 int  b200_csr_nrows(const b200_csr* M);
 int  b200_csr_ncols(const b200_csr* M);
 int  b200_csr_nnz(const b200_csr* M);

@@ -1,0 +1,245 @@
+// transpose.cu -- CSR of the transpose, built on the device.
+//
+// The user's CSC arrays of A are the CSR of A' (uploaded once); the solver also needs CSR(A) for
+// A x.  Building it on the host (a parallel stable counting sort, algebra/b200/matrix.c) and
+// uploading a second 12-byte-per-entry copy cost 45 + 14 ms of the 97 ms osqp_setup on the
+// 1.14e7-nnz Lasso; here it is five kernels over data that is already in HBM:
+//   count     row lengths of the transpose (integer atomics: order-independent result)
+//   scan      three-kernel inclusive prefix sum -> row_ptr, and the longest row
+//   scatter   every entry takes the next free slot of its destination row (atomic cursor)
+//   sort      one warp per destination row puts its entries in ascending column order by RANK
+//             (rank = number of entries of the row with a smaller (column, source position)), so
+//             the result does not depend on the order in which the atomics were served:
+//             bit-identical to the host sort, run-to-run deterministic
+//   gather    values through the recorded source positions; map[k] = final position of entry k
+//             (device-resident index map for OSQPMatrix_update_values)
+// Role in the reference: csr_transpose / csr_from_csc of algebra/cuda/src/cuda_csr.cu:489-628,
+// which sorts with thrust and calls cusparseCsr2cscEx2.
+#include "csr.cuh"
+
+#include <vector>
+
+using namespace b200;
+
+namespace {
+
+constexpr int kSortMaxRow  = 4096;   // longer destination rows: the caller keeps the host path
+constexpr int kScanBlock   = 1024;
+constexpr int kScanPerThr  = 4;
+constexpr int kScanChunk   = kScanBlock * kScanPerThr;
+
+__global__ void __launch_bounds__(kBlock) tr_count(int nnz, const int* __restrict__ col, int* cnt) {
+  const int stride = gridDim.x * blockDim.x;
+  for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < nnz; k += stride) atomicAdd(&cnt[col[k] + 1], 1);
+}
+
+// CTA-wide inclusive scan of one value per thread; returns the inclusive prefix, total in `tot`
+__device__ __forceinline__ int block_scan_incl(int v, int* sh /* >= 33 */, int& tot) {
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int t = __shfl_up_sync(0xffffffffu, v, o);
+    if (lane >= o) v += t;
+  }
+  __syncthreads();
+  if (lane == 31) sh[w] = v;
+  __syncthreads();
+  if (w == 0) {
+    int s = (lane < (int)(blockDim.x >> 5)) ? sh[lane] : 0;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int t = __shfl_up_sync(0xffffffffu, s, o);
+      if (lane >= o) s += t;
+    }
+    sh[lane] = s;
+  }
+  __syncthreads();
+  tot = sh[(blockDim.x >> 5) - 1];
+  return v + (w > 0 ? sh[w - 1] : 0);
+}
+
+// phase 1: totals of the kScanChunk-sized chunks (+ the largest single count)
+__global__ void __launch_bounds__(kScanBlock) scan_totals(int n, const int* __restrict__ in, int* totals, int* maxval) {
+  __shared__ int sh[33];
+  const int base = blockIdx.x * kScanChunk + threadIdx.x * kScanPerThr;
+  int s = 0, mx = 0;
+#pragma unroll
+  for (int u = 0; u < kScanPerThr; u++)
+    if (base + u < n) { const int v = in[base + u]; s += v; mx = v > mx ? v : mx; }
+  int tot;
+  block_scan_incl(s, sh, tot);
+  for (int o = 16; o > 0; o >>= 1) mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  if ((threadIdx.x & 31) == 0 && mx > 0) atomicMax(maxval, mx);
+  if (threadIdx.x == 0) totals[blockIdx.x] = tot;
+}
+// phase 2: exclusive scan of the chunk totals by one CTA
+__global__ void __launch_bounds__(kScanBlock) scan_offsets(int nb, int* totals) {
+  __shared__ int sh[33];
+  __shared__ int carry;
+  if (threadIdx.x == 0) carry = 0;
+  __syncthreads();
+  for (int b0 = 0; b0 < nb; b0 += kScanBlock) {
+    const int i = b0 + threadIdx.x;
+    const int v = i < nb ? totals[i] : 0;
+    int tot;
+    const int inc = block_scan_incl(v, sh, tot);
+    if (i < nb) totals[i] = carry + inc - v;
+    __syncthreads();
+    if (threadIdx.x == 0) carry += tot;
+    __syncthreads();
+  }
+}
+// phase 3: inclusive scan inside every chunk + its offset, in place
+__global__ void __launch_bounds__(kScanBlock) scan_apply(int n, int* data, const int* __restrict__ offsets) {
+  __shared__ int sh[33];
+  const int base = blockIdx.x * kScanChunk + threadIdx.x * kScanPerThr;
+  int v[kScanPerThr], s = 0;
+#pragma unroll
+  for (int u = 0; u < kScanPerThr; u++) { v[u] = (base + u < n) ? data[base + u] : 0; s += v[u]; }
+  int tot;
+  int run = block_scan_incl(s, sh, tot) - s + offsets[blockIdx.x];
+#pragma unroll
+  for (int u = 0; u < kScanPerThr; u++) {
+    run += v[u];
+    if (base + u < n) data[base + u] = run;
+  }
+}
+
+// one warp per SOURCE row j: entry k of column i goes to the next free slot of destination row i
+__global__ void __launch_bounds__(kBlock) tr_scatter(int nrows_src, const int* __restrict__ rp_src,
+                                                     const int* __restrict__ col_src, int* cursor,
+                                                     int* tmp_col, int* tmp_src) {
+  const int lane = threadIdx.x & 31, wpb = kBlock >> 5;
+  for (int j = blockIdx.x * wpb + (threadIdx.x >> 5); j < nrows_src; j += gridDim.x * wpb) {
+    const int s = rp_src[j], e = rp_src[j + 1];
+    for (int k = s + lane; k < e; k += 32) {
+      const int pos = atomicAdd(&cursor[col_src[k]], 1);
+      tmp_col[pos] = j;
+      tmp_src[pos] = k;
+    }
+  }
+}
+
+// one warp per DESTINATION row: rank-sort by (column, source position); gather the values
+__global__ void __launch_bounds__(kBlock) tr_sort_rows(int nrows, const int* __restrict__ rp,
+                                                       const int* __restrict__ tmp_col, const int* __restrict__ tmp_src,
+                                                       const T* __restrict__ val_src, int* col, T* val, int* map) {
+  const int lane = threadIdx.x & 31, wpb = kBlock >> 5;
+  for (int i = blockIdx.x * wpb + (threadIdx.x >> 5); i < nrows; i += gridDim.x * wpb) {
+    const int base = rp[i], len = rp[i + 1] - base;
+    if (len <= 32) {
+      const int c = lane < len ? tmp_col[base + lane] : 0x7fffffff;
+      const int s = lane < len ? tmp_src[base + lane] : 0x7fffffff;
+      int rank = 0;
+      for (int t = 0; t < len; t++) {
+        const int ct = __shfl_sync(0xffffffffu, c, t), st = __shfl_sync(0xffffffffu, s, t);
+        rank += (ct < c) || (ct == c && st < s);
+      }
+      if (lane < len) {
+        col[base + rank] = c;
+        val[base + rank] = val_src[s];
+        if (map) map[s] = base + rank;
+      }
+    } else {
+      for (int e = lane; e < len; e += 32) {
+        const int c = tmp_col[base + e], s = tmp_src[base + e];
+        int rank = 0;
+        for (int t = 0; t < len; t++) {
+          const int ct = tmp_col[base + t], st = tmp_src[base + t];
+          rank += (ct < c) || (ct == c && st < s);
+        }
+        col[base + rank] = c;
+        val[base + rank] = val_src[s];
+        if (map) map[s] = base + rank;
+      }
+    }
+  }
+}
+
+__global__ void __launch_bounds__(kBlock) veci_gather_kernel(int* dst, const int* __restrict__ src,
+                                                             const int* __restrict__ idx, int n) {
+  const int stride = gridDim.x * blockDim.x;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) dst[i] = src[idx[i]];
+}
+
+}  // namespace
+
+extern "C" {
+
+// CSR of the transpose of Mt (Mt: r x c  ->  result: c x r), columns ascending inside every row.
+// *d_map_out (optional) receives a device array with, for every stored entry k of Mt, its position
+// in the result; the caller frees it with b200_free.  Returns NULL when the result has a row longer
+// than kSortMaxRow or on failure -- the caller then keeps its host path.
+b200_csr* b200_csr_transpose(const b200_csr* Mt, int** d_map_out) {
+  Context& c = ctx();
+  cudaStream_t st = c.stream;
+  if (d_map_out) *d_map_out = nullptr;
+  if (!Mt || Mt->nnz <= 0 || Mt->ncols <= 0) return nullptr;
+  const int nr = Mt->ncols, nc = Mt->nrows, nnz = Mt->nnz;
+  b200_csr* M = new b200_csr();
+  M->nrows = nr; M->ncols = nc; M->nnz = nnz;
+  int *d_tot = nullptr, *d_max = nullptr, *d_cursor = nullptr, *d_tcol = nullptr, *d_tsrc = nullptr, *d_map = nullptr;
+  const int nscan = nr + 1, nchunks = (nscan + kScanChunk - 1) / kScanChunk;
+  bool ok = true;
+  ok &= B200_CHECK(dev_malloc(&M->d_row_ptr, sizeof(int) * ((size_t)nr + 2 * kPad)));
+  ok &= B200_CHECK(dev_malloc(&M->d_col_ind, sizeof(int) * ((size_t)nnz + 2 * kPad)));
+  ok &= B200_CHECK(dev_malloc(&M->d_val, sizeof(T) * ((size_t)nnz + 2 * kPad)));
+  ok &= B200_CHECK(dev_malloc(&d_tot, sizeof(int) * ((size_t)nchunks + 1)));
+  ok &= B200_CHECK(dev_malloc(&d_max, sizeof(int)));
+  ok &= B200_CHECK(dev_malloc(&d_cursor, sizeof(int) * ((size_t)nr + 1)));
+  ok &= B200_CHECK(dev_malloc(&d_tcol, sizeof(int) * ((size_t)nnz + 1)));
+  ok &= B200_CHECK(dev_malloc(&d_tsrc, sizeof(int) * ((size_t)nnz + 1)));
+  if (d_map_out) ok &= B200_CHECK(dev_malloc(&d_map, sizeof(int) * ((size_t)nnz + 1)));
+  int h_max = 0;
+  std::vector<int> h_rp;
+  if (ok) {
+    ok &= B200_CHECK(cudaMemsetAsync(M->d_row_ptr, 0, sizeof(int) * ((size_t)nr + 1), st));
+    ok &= B200_CHECK(cudaMemsetAsync(d_max, 0, sizeof(int), st));
+    const int cap = c.sm_count * 8;
+    int g = (nnz + kBlock - 1) / kBlock;
+    tr_count<<<g < cap ? g : cap, kBlock, 0, st>>>(nnz, Mt->d_col_ind, M->d_row_ptr);
+    count_launch();
+    scan_totals<<<nchunks, kScanBlock, 0, st>>>(nscan, M->d_row_ptr, d_tot, d_max);
+    count_launch();
+    scan_offsets<<<1, kScanBlock, 0, st>>>(nchunks, d_tot);
+    count_launch();
+    scan_apply<<<nchunks, kScanBlock, 0, st>>>(nscan, M->d_row_ptr, d_tot);
+    count_launch();
+    h_rp.resize((size_t)nr + 1);
+    ok &= B200_CHECK(cudaMemcpyAsync(&h_max, d_max, sizeof(int), cudaMemcpyDeviceToHost, st));
+    ok &= B200_CHECK(cudaMemcpyAsync(h_rp.data(), M->d_row_ptr, sizeof(int) * ((size_t)nr + 1), cudaMemcpyDeviceToHost, st));
+    ok &= B200_CHECK(cudaMemcpyAsync(d_cursor, M->d_row_ptr, sizeof(int) * (size_t)nr, cudaMemcpyDeviceToDevice, st));
+    ok &= B200_CHECK(cudaStreamSynchronize(st));
+  }
+  if (ok && h_max <= kSortMaxRow && h_rp[nr] == nnz) {
+    const int wpb = kBlock >> 5, cap = c.sm_count * 8;
+    int g1 = (nc + wpb - 1) / wpb, g2 = (nr + wpb - 1) / wpb;
+    tr_scatter<<<g1 < cap ? g1 : cap, kBlock, 0, st>>>(nc, Mt->d_row_ptr, Mt->d_col_ind, d_cursor, d_tcol, d_tsrc);
+    count_launch();
+    tr_sort_rows<<<g2 < cap ? g2 : cap, kBlock, 0, st>>>(nr, M->d_row_ptr, d_tcol, d_tsrc, Mt->d_val, M->d_col_ind,
+                                                      M->d_val, d_map);
+    count_launch();
+    ok = b200_build_schedule(M, h_rp.data()) == 0;    // synchronises the stream
+  } else {
+    ok = false;
+  }
+  dev_free(d_tot); dev_free(d_max); dev_free(d_cursor); dev_free(d_tcol); dev_free(d_tsrc);
+  if (!ok) {
+    dev_free(d_map);
+    b200_csr_destroy(M);
+    return nullptr;
+  }
+  if (d_map_out) *d_map_out = d_map;
+  return M;
+}
+
+// dst[i] = src[idx[i]] for integer arrays (index maps of OSQPMatrix_update_values)
+void b200_veci_gather(int* dst, const int* src, const int* idx, int n) {
+  if (n <= 0) return;
+  const int cap = ctx().sm_count * 8;
+  const int g = (n + kBlock - 1) / kBlock;
+  veci_gather_kernel<<<g < cap ? g : cap, kBlock, 0, ctx().stream>>>(dst, src, idx, n);
+  count_launch();
+}
+
+}  // extern "C"

@@ -56,6 +56,8 @@ def kernels(precision="f64"):
         "b200_vec_bounds_type": (i, [ip, vp, vp, F, F, i]),
         "b200_csr_create": (vp, [i, i, i, ip, ip, vp]),
         "b200_csr_destroy": (None, [vp]),
+        "b200_csr_transpose": (vp, [vp, C.POINTER(C.c_void_p)]),
+        "b200_veci_gather": (None, [ip, ip, ip, i]),
         "b200_csr_nrows": (i, [vp]), "b200_csr_ncols": (i, [vp]), "b200_csr_nnz": (i, [vp]),
         "b200_csr_values": (vp, [vp]),
         "b200_csr_download": (i, [vp, ip, ip, vp]),

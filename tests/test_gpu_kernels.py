@@ -246,3 +246,49 @@ def test_full_size_spmv_properties(kern):
     assert np.abs(dAx2.get()[rows] - (A[rows] @ (2 * x + 3 * x2))).max() < 1e-10
     k.b200_csr_destroy(hA)
     k.b200_csr_destroy(hAt)
+
+
+@pytest.mark.parametrize("shape,density", [((300, 70), 0.1), ((2000, 500), 0.02), ((64, 4000), 0.3), ((50, 50), 0.0)])
+def test_device_transpose_matches_host_order(kern, shape, density):
+    """b200_csr_transpose: CSR of the transpose built on the device (count / scan / scatter / per-row
+    rank sort) must be bit-identical to the sorted host transpose, whatever order the atomics were
+    served in, and the index map must send every source entry to its copy."""
+    k = kern
+    rng = np.random.default_rng(7)
+    M = sp.random(shape[0], shape[1], density=density, format="csr", random_state=3,
+                  data_rvs=lambda s: rng.standard_normal(s))
+    if density == 0.0:
+        M = sp.csr_matrix(([1.5, -2.5], ([3, 3], [7, 1])), shape=shape)    # nearly empty: empty rows on both sides
+    M.sort_indices()
+    h = csr_to_device(k, M)
+    d_map = C.c_void_p()
+    ht = k.b200_csr_transpose(h, C.byref(d_map))
+    assert ht, "device transpose refused a matrix with short rows"
+    Mt = sp.csr_matrix(M.T)
+    Mt.sort_indices()
+    rp = np.zeros(Mt.shape[0] + 1, dtype=np.int32)
+    ci = np.zeros(max(Mt.nnz, 1), dtype=np.int32)
+    vx = np.zeros(max(Mt.nnz, 1), dtype=np.float64)
+    assert k.b200_csr_download(ht, rp.ctypes.data, ci.ctypes.data, vx.ctypes.data) == 0
+    assert np.array_equal(rp, Mt.indptr) and np.array_equal(ci[:Mt.nnz], Mt.indices)
+    assert np.array_equal(vx[:Mt.nnz], Mt.data)                       # values moved, not recomputed
+    mp = np.zeros(M.nnz, dtype=np.int32)
+    assert k.b200_copy_out(mp.ctypes.data, d_map, M.nnz * 4) == 0
+    assert np.array_equal(vx[mp], M.data) and np.unique(mp).size == M.nnz
+    # twice the same bits
+    ht2 = k.b200_csr_transpose(h, None)
+    ci2, vx2 = np.zeros_like(ci), np.zeros_like(vx)
+    assert k.b200_csr_download(ht2, rp.ctypes.data, ci2.ctypes.data, vx2.ctypes.data) == 0
+    assert np.array_equal(ci, ci2) and np.array_equal(vx, vx2)
+    k.b200_free(d_map)
+    for hh in (h, ht, ht2):
+        k.b200_csr_destroy(hh)
+
+
+def test_device_transpose_declines_over_long_rows(kern):
+    """A destination row longer than the rank-sort limit keeps the host path (NULL, no crash)."""
+    k = kern
+    M = sp.csr_matrix(np.ones((5000, 3)))           # transpose has rows of 5000 entries
+    h = csr_to_device(k, M)
+    assert not k.b200_csr_transpose(h, None)
+    k.b200_csr_destroy(h)
