@@ -343,7 +343,9 @@ def run_b200(args):
     barrier()
     e_total = time.perf_counter() - t0
     fi = F if prec == "f64" else 4
-    h2d = 2 * nnzA * (fi + 4) + (n + m + 2) * 4 + (2 * nnzP + n) * (fi + 4) + (n + 2 * m) * fi
+    # uploads of one setup: CSC(A) once (= CSR(A'); CSR(A) is built on the device), the full symmetric
+    # P expanded on the host, q / l / u
+    h2d = nnzA * (fi + 4) + (n + 1) * 4 + (2 * nnzP + n) * (fi + 4) + (n + 1) * 4 + (n + 2 * m) * fi
     d2h = 2 * (n + m) * fi
 
     # ---- aggregate over ranks: max time, summed work

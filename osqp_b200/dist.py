@@ -165,6 +165,28 @@ def shard_problem_split(pb, rank, plan):
                 n_shared=int(plan["shared"].size))
 
 
+def assemble_solution(parts, n_global, m_global, plan=None, bounds=None):
+    """Global (x, y) from the per-rank (x_r, y_r) pairs.  Column-split layout (`plan`): x_r is
+    [shared slice ; owned slice] in the order of plan["cols"][r] (the shared slice is taken from rank
+    0), y_r the rows plan["rows"][r] (a padded free row, if any, is dropped).  Plain row blocks
+    (`bounds`): x replicated, y_r the contiguous block of rank r."""
+    x, y = np.zeros(n_global), np.zeros(m_global)
+    if plan is not None:
+        ns = plan["shared"].size
+        for rk, (xr, yr) in enumerate(parts):
+            rows, cols = plan["rows"][rk], plan["cols"][rk]
+            if rk == 0:
+                x[cols] = xr
+            else:
+                x[cols[ns:]] = xr[ns:]
+            y[rows] = yr[:len(rows)]
+    else:
+        x[:] = parts[0][0]
+        for rk, (_, yr) in enumerate(parts):
+            y[int(bounds[rk]):int(bounds[rk + 1])] = yr
+    return x, y
+
+
 def exchange_unique_id(make_id, dist):
     """rank 0 creates the NCCL unique id, everybody receives it (works on any backend)."""
     import torch
@@ -239,21 +261,8 @@ class ShardedOSQP(OSQP):
         """Global (x, y) from the per-rank results `r` (collective; every rank gets the same arrays)."""
         parts = [None] * self.world
         dist.all_gather_object(parts, (np.asarray(r.x), np.asarray(r.y)))
-        x, y = np.zeros(self.n_global), np.zeros(self.m_global)
-        if self.plan is not None:
-            for rk, (xr, yr) in enumerate(parts):
-                rows, cols = self.plan["rows"][rk], self.plan["cols"][rk]
-                ns = self.plan["shared"].size
-                if rk == 0:
-                    x[cols] = xr
-                else:
-                    x[cols[ns:]] = xr[ns:]
-                y[rows] = yr[:len(rows)]
-        else:
-            x[:] = parts[0][0]
-            for rk, (_, yr) in enumerate(parts):
-                y[int(self.bounds[rk]):int(self.bounds[rk + 1])] = yr
-        return x, y
+        return assemble_solution(parts, self.n_global, self.m_global, plan=self.plan,
+                                 bounds=getattr(self, "bounds", None))
 
     def cleanup(self):
         super().cleanup()

@@ -122,3 +122,65 @@ def test_column_split_plan_partitions_the_problem(family, world):
         assert ns <= 50 and ns < 0.2 * n
     else:
         assert ns == n                                          # no low-degree cut: falls back to row blocks
+
+
+SPLIT_WORKER = textwrap.dedent("""
+    import os, sys
+    sys.path.insert(0, {root!r})
+    import numpy as np, scipy.sparse as sp, torch, torch.distributed as dist
+    from osqp_b200 import problems
+    from osqp_b200.dist import plan_column_split, shard_problem_split, assemble_solution
+    dist.init_process_group("gloo")
+    rank, world = dist.get_rank(), dist.get_world_size()
+    pb = problems.huber(15, 300, density=0.15, seed=4)
+    A = sp.csr_matrix(pb["A"]); n, m = A.shape[1], A.shape[0]
+    plan = plan_column_split(pb["P"], pb["A"], world)
+    sh = shard_problem_split(pb, rank, plan)
+    ns = plan["shared"].size
+    rng = np.random.default_rng(11)                       # same "solution" on every rank
+    x_true, y_true = rng.standard_normal(n), rng.standard_normal(m)
+    rows, cols = plan["rows"][rank], plan["cols"][rank]
+    x_loc = x_true[cols]
+    y_loc = np.concatenate([y_true[rows], np.zeros(sh["padded"])])
+    # rule 1 (algebra/b200/vector.c DIST_REDUCE): a reduction over a column vector counts the shared
+    # slice on rank 0 only, then the ranks are summed / maxed
+    off = 0 if rank == 0 else ns
+    t = torch.tensor([float(sh["q"][off:] @ x_loc[off:])], dtype=torch.float64)
+    dist.all_reduce(t)
+    assert abs(t.item() - float(pb["q"] @ x_true)) < 1e-9 * max(1.0, abs(float(pb["q"] @ x_true)))
+    mx = torch.tensor([float(np.abs(x_loc[off:]).max()) if x_loc[off:].size else 0.0], dtype=torch.float64)
+    dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+    assert mx.item() == float(np.abs(x_true).max())
+    # rule 2 (matrix.c Atxpy / pcg_graph.cu exchange_vector): A_r' y_r is complete on the owned columns
+    # and needs a sum over the ranks on the shared head only
+    part = sh["A"].T @ y_loc
+    head = torch.from_numpy(part[:ns].copy())
+    dist.all_reduce(head)
+    full = A.T @ y_true
+    assert np.allclose(head.numpy(), full[plan["shared"]], rtol=1e-12, atol=1e-12)
+    assert np.allclose(part[ns:], full[cols[ns:]], rtol=1e-12, atol=1e-12)
+    # rule 3: A_r x_r needs no exchange at all
+    assert np.allclose((sh["A"] @ x_loc)[:len(rows)], (A @ x_true)[rows], rtol=1e-12, atol=1e-12)
+    # assembly of the global solution from the per-rank slices
+    parts = [None] * world
+    dist.all_gather_object(parts, (x_loc, y_loc))
+    x, y = assemble_solution(parts, n, m, plan=plan)
+    assert np.array_equal(x, x_true) and np.array_equal(y, y_true)
+    dist.barrier()
+    if rank == 0:
+        print("SPLIT_WORKER_OK", ns, n)
+    dist.destroy_process_group()
+""")
+
+
+def test_gloo_column_split_layout_rules(tmp_path):
+    """world_size 2 on CPU: the three exchange rules of the column-split layout (reductions count the
+    shared slice once; A'y is exchanged on the shared head only; A x needs nothing) and the assembly
+    of the global solution."""
+    script = tmp_path / "split_worker.py"
+    script.write_text(SPLIT_WORKER.format(root=str(ROOT)))
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1")
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                          "--master-addr", "127.0.0.1", "--master-port", "29534", str(script)],
+                         capture_output=True, text=True, env=env, timeout=300)
+    assert "SPLIT_WORKER_OK" in out.stdout, out.stdout[-2000:] + out.stderr[-2000:]
