@@ -43,6 +43,7 @@ struct Context {
   char         name[256]  = {0};
   int          trace_on   = 0;   // B200_TRACE_FILE: one CUDA event + host timestamp per launch
   int          slot       = 0;   // index of this context (per-context __constant__ argument blocks)
+  int          args_valid = 0;   // the constant block of this slot holds the last PcgArgs this thread copied
 };
 
 // ONE CONTEXT PER HOST THREAD (thread_local): its own stream, reduction workspace and result

@@ -156,6 +156,7 @@ int b200_init(int device) {
   c.launches   = 0;
   c.refcount   = 1;
   c.trace_on   = getenv("B200_TRACE_FILE") ? 1 : 0;
+  c.args_valid = 0;
   return 0;
 }
 

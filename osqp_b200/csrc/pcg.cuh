@@ -1,9 +1,11 @@
 // pcg.cuh -- state shared by the two device-resident PCG drivers:
+//   pcg_graph.cu  lean 512-thread passes; the CG loop is a CUDA-graph WHILE node whose condition is
+//                 set on the device (no host synchronisation); loop body = A pass, fused-operator
+//                 pass with three dots, ONE x/r/p update.  Default from kGraphDriverMinNnz stored
+//                 entries.  Also hosts the row-sharded (multi-GPU) driver, which runs the same
+//                 kernels from a host loop with the exchanges in between.
 //   pcg.cu        one persistent cooperative kernel per solve (grid.sync between phases); lowest
-//                 launch latency, used for small problems
-//   pcg_graph.cu  lean one-CTA-per-tile kernels; the CG loop is a CUDA-graph WHILE node whose
-//                 condition is set on the device, so there is still no host synchronisation;
-//                 higher occupancy per pass, used for large problems
+//                 launch count, default for small problems
 #pragma once
 
 #include "csr.cuh"

@@ -119,11 +119,25 @@ __device__ __forceinline__ bool publish_fold(const double* part, const int* slot
 // one extra L1 wavefront per use in the per-row epilogues: 17 us of a 70 us pass.)
 __constant__ PcgArgs c_args[kMaxContexts];   // one block per library context (host thread)
 
-inline bool set_args(const PcgArgs& a, cudaStream_t st) {
-  // pageable source: the runtime stages the 300 bytes before returning; stream-ordered with the
+inline bool set_args(const PcgArgs& a_in, cudaStream_t st) {
+  // Between two termination checks consecutive solves of an ADMM run have identical argument
+  // blocks (same vectors, same rho, prim_res / dual_res refreshed only at the checks; admm_iter is
+  // only ever tested for == 1): the ~8 us constant-memory copy is skipped when nothing changed.
+  static thread_local PcgArgs last;
+  static thread_local bool have_last = false;
+  static thread_local int last_slot = -1;
+  PcgArgs a = a_in;
+  if (a.admm_iter > 2) a.admm_iter = 2;
+  if (have_last && ctx().args_valid && last_slot == ctx().slot && memcmp(&last, &a, sizeof(PcgArgs)) == 0) return true;
+  // pageable source: the runtime stages the bytes before returning; stream-ordered with the
   // kernels of the previous solve
-  return B200_CHECK(cudaMemcpyToSymbolAsync(c_args, &a, sizeof(PcgArgs), sizeof(PcgArgs) * (size_t)ctx().slot,
-                                            cudaMemcpyHostToDevice, st));
+  const bool ok = B200_CHECK(cudaMemcpyToSymbolAsync(c_args, &a, sizeof(PcgArgs), sizeof(PcgArgs) * (size_t)ctx().slot,
+                                                     cudaMemcpyHostToDevice, st));
+  last = a;
+  last_slot = ctx().slot;
+  have_last = ok;
+  ctx().args_valid = ok ? 1 : 0;
+  return ok;
 }
 
 // step length and (predicted) direction coefficient of one CG iteration, from the three dots of
@@ -567,50 +581,6 @@ __global__ void g_loop_init(int slot, PcgRun* run, cudaGraphConditionalHandle h)
   cudaGraphSetConditional(h, (run->rnorm > run->eps && run->it < c_args[slot].max_iter) ? 1u : 0u);
 }
 
-// L3: x += a p ; r += a Kp ; Ax += a w ; totals r'y, ||r||_inf ; last CTA: beta, it++, condition
-__global__ void __launch_bounds__(kBlock) g_update(int slot, PcgRun* run, double* red, int stride,
-                                                   cudaGraphConditionalHandle h) {
-  __shared__ double shr[33];
-  const PcgArgs& a = c_args[slot];
-  const int n = a.n, m = a.m;
-  const T alpha = (T)(run->rTy / run->pKp);
-  const int gtid = blockIdx.x * blockDim.x + threadIdx.x, gstride = gridDim.x * blockDim.x;
-  double acc_rty = 0.0, acc_max = 0.0;
-  for (int i = gtid; i < n; i += gstride) {
-    a.x[i] += alpha * a.p[i];
-    const T rr = a.r[i] + alpha * a.Kp[i];
-    a.r[i] = rr;
-    const T yy = a.minv[i] * rr;
-    acc_rty += (double)rr * (double)yy;
-    acc_max = fmax(acc_max, fabs((double)rr));
-  }
-  for (int j = gtid; j < m; j += gstride) a.Ax[j] += alpha * a.w[j];
-  acc_rty = block_sum(acc_rty, shr);
-  acc_max = block_max(acc_max, shr);
-  double tot;
-  publish<true>(acc_max, red, stride, SLOT_RMAX, nullptr, false, shr, tot);
-  if (publish<false>(acc_rty, red, stride, SLOT_RTY, &run->ticket[SLOT_RTY], true, shr, tot)) {
-    const double rmax = fold<true>(red, stride, SLOT_RMAX, shr);
-    if (threadIdx.x == 0) {
-      run->beta  = tot / run->rTy;
-      run->rTy   = tot;
-      run->rnorm = rmax;
-      run->it   += 1;
-      run->ticket[SLOT_RTY] = 0;
-      if (h) cudaGraphSetConditional(h, (rmax > run->eps && run->it < a.max_iter) ? 1u : 0u);
-    }
-  }
-}
-
-// L4: p = beta p - M^-1 r
-__global__ void __launch_bounds__(kBlock) g_direction(int slot, const PcgRun* run) {
-  const PcgArgs& a = c_args[slot];
-  const T beta = (T)run->beta;
-  const int stride = gridDim.x * blockDim.x;
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < a.n; i += stride)
-    a.p[i] = beta * a.p[i] - a.minv[i] * a.r[i];
-}
-
 // L3+L4 in one kernel (graph driver): x += a p ; r += a Kp ; p = beta p - M^-1 r ; Ax += a w ;
 // totals r'y (exact), ||r||_inf ; last CTA: it++, loop condition.  8 n F + 3 m F bytes.
 __global__ void __launch_bounds__(kBlock) g_update_fused(int slot, PcgRun* run, double* red, int stride,
@@ -1030,8 +1000,8 @@ extern "C" int b200_pcg_profile_last(int reps, double* out_us, int nout) {
   out_us[5]  = timeit([&] { g_lean_pass<2><<<lean_grid(s->K2), kLeanBlock, 0, st>>>(d_args, run, red, cap); });
   out_us[6]  = timeit([&] { if (m > 0) g_p1_carried<<<ew_grid(m), kBlock, 0, st>>>(d_args); });
   out_us[7]  = timeit([&] { g_epilogue<<<ew_grid(nm), kBlock, 0, st>>>(d_args, run); });
-  out_us[8]  = timeit([&] { g_update<<<gu, kBlock, 0, st>>>(d_args, run, red, cap, none); });
-  out_us[9]  = timeit([&] { g_direction<<<ew_grid(n), kBlock, 0, st>>>(d_args, run); });
+  out_us[8]  = 0.0;   // (slots of the retired two-kernel L3 / L4 update)
+  out_us[9]  = 0.0;
   out_us[10] = timeit([&] { g_nop<<<1, 32, 0, st>>>(); });   // launch floor
   out_us[11] = timeit([&] { if (m > 0) g_lean_pass<3><<<lean_grid(*s->A, false), kLeanBlock, 0, st>>>(d_args, run, red, cap); });
   if (nout >= 14) {

@@ -54,7 +54,7 @@ def child(args):
         buf = (C.c_double * 14)()
         rc = k.b200_pcg_profile_last(20, buf, 14)
         names = ["lean_A(L1)", "lean_K2(L2,3dots)", "update_fused(L3+L4)", "seq A+K2+update", "generic K<0>(P2)",
-                 "lean K2 P2", "p1_carried", "epilogue", "old update(L3)", "old direction(L4)", "nop launch",
+                 "lean K2 P2", "p1_carried", "epilogue", "(retired)", "(retired) ", "nop launch",
                  "lean A exact", "lean At plain", "lean K2 plain"]
         out["phase_us"] = {nm: round(buf[i], 2) for i, nm in enumerate(names)} if rc == 0 else f"rc={rc}"
     s.cleanup()     # last solver alive: b200_shutdown dumps the launch trace
