@@ -42,7 +42,8 @@ struct OSQPMatrix_ {
   OSQPInt   is_symmetric;
   OSQPInt*  h_map;    /* user CSC k -> position in S (A: CSR pos; P: upper copy) */
   OSQPInt*  h_map2;   /* P only: position of the mirrored copy, -1 on diagonal   */
-  OSQPInt*  d_map;    /* A built by the device transpose: the same map as h_map, in HBM (h_map NULL) */
+  OSQPInt*  d_map;    /* built on the device: the same map as h_map, in HBM (h_map NULL)   */
+  OSQPInt*  d_map2;   /* P built on the device: the same map as h_map2, in HBM             */
 };
 
 /*

@@ -238,12 +238,19 @@ OSQPMatrix* OSQPMatrix_new_from_csc(const OSQPCscMatrix* M, OSQPInt is_triu) {
   out->is_symmetric = is_triu ? 1 : 0;
 
   if (is_triu) {
-    out->h_map = (OSQPInt*)c_malloc(((size_t)nnz + 1) * sizeof(OSQPInt));
-    if (!out->h_map) goto fail;
-    out->h_map2 = (OSQPInt*)c_malloc(((size_t)nnz + 1) * sizeof(OSQPInt));
-    if (!out->h_map2) goto fail;
-    out->S  = full_from_triu(M->n, M->p, M->i, M->x, out->h_map, out->h_map2);
     out->St = OSQP_NULL;
+    /* symmetric expansion on the device (upload the triangle once, transpose, merge); the host
+       expansion remains for over-long rows, empty matrices and B200_HOST_TRANSPOSE=1 */
+    if (!getenv("B200_HOST_TRANSPOSE"))
+      out->S = b200_csr_symmetric_from_triu((int)M->n, M->p, M->i, M->x, &out->d_map, &out->d_map2);
+    if (!out->S) {
+      out->d_map = out->d_map2 = OSQP_NULL;
+      out->h_map = (OSQPInt*)c_malloc(((size_t)nnz + 1) * sizeof(OSQPInt));
+      if (!out->h_map) goto fail;
+      out->h_map2 = (OSQPInt*)c_malloc(((size_t)nnz + 1) * sizeof(OSQPInt));
+      if (!out->h_map2) goto fail;
+      out->S = full_from_triu(M->n, M->p, M->i, M->x, out->h_map, out->h_map2);
+    }
     if (!out->S) goto fail;
   } else {
     /* CSC(A) == CSR(A') */
@@ -277,6 +284,7 @@ void OSQPMatrix_free(OSQPMatrix* M) {
     c_free(M->h_map);
     c_free(M->h_map2);
     b200_free(M->d_map);
+    b200_free(M->d_map2);
     c_free(M);
   }
 }
@@ -315,17 +323,24 @@ void OSQPMatrix_update_values(OSQPMatrix* M, const OSQPFloat* Mx_new, const OSQP
   b200_copy_in(d_x, Mx_new, (size_t)cnt * sizeof(OSQPFloat));
 
   if (M->d_map) {
-    /* A with a device-resident index map: positions are looked up in HBM */
+    /* device-resident index maps: positions are looked up in HBM.  A: position in CSR(A), and the
+       user's own ordering for A'.  P: the entry itself and its mirror (-1 on the diagonal). */
     if (!Mx_new_idx) {
       b200_vec_scatter(b200_csr_values(M->S), d_x, M->d_map, (int)cnt);
-      b200_copy_in(b200_csr_values(M->St), d_x, (size_t)cnt * sizeof(OSQPFloat));
+      if (M->is_symmetric) b200_vec_scatter_nonneg(b200_csr_values(M->S), d_x, M->d_map2, (int)cnt);
+      else b200_copy_in(b200_csr_values(M->St), d_x, (size_t)cnt * sizeof(OSQPFloat));
     } else {
       OSQPInt* d_pos = (OSQPInt*)b200_malloc((size_t)cnt * sizeof(OSQPInt));
       if (!d_pos) goto done;
       b200_copy_in(d_idx, Mx_new_idx, (size_t)cnt * sizeof(OSQPInt));
       b200_veci_gather(d_pos, M->d_map, d_idx, (int)cnt);
       b200_vec_scatter(b200_csr_values(M->S), d_x, d_pos, (int)cnt);
-      b200_vec_scatter(b200_csr_values(M->St), d_x, d_idx, (int)cnt);
+      if (M->is_symmetric) {
+        b200_veci_gather(d_pos, M->d_map2, d_idx, (int)cnt);
+        b200_vec_scatter_nonneg(b200_csr_values(M->S), d_x, d_pos, (int)cnt);
+      } else {
+        b200_vec_scatter(b200_csr_values(M->St), d_x, d_idx, (int)cnt);
+      }
       b200_free(d_pos);
     }
     goto done;

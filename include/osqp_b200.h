@@ -141,6 +141,15 @@ void b200_csr_destroy(b200_csr* M);
  * replaces csr_transpose (algebra/cuda/src/cuda_csr.cu:489-560: thrust sort + cusparseCsr2cscEx2) */
 b200_csr* b200_csr_transpose(const b200_csr* Mt, int** d_map_out);
 void b200_veci_gather(int* d_dst, const int* d_src, const int* d_idx, int n);
+/* Full symmetric CSR (structurally full diagonal: lower mirrors ++ zero diagonal if missing ++ upper
+ * triangle, per row) from the upper-triangular CSC arrays of P (host pointers), expanded on the
+ * device.  *d_map_u / *d_map_l: device arrays of nnz ints, position of every user entry itself and
+ * of its mirror (-1 for diagonal entries); free with b200_free.  NULL = caller keeps its host path.
+ * replaces csr_triu_to_full / csr_expand of algebra/cuda/src/cuda_csr.cu:562-628 */
+b200_csr* b200_csr_symmetric_from_triu(int n, const int* h_p, const int* h_i, const b200_float* h_x,
+                                       int** d_map_u, int** d_map_l);
+/* d_dst[d_idx[i]] = d_src[i] for the i with d_idx[i] >= 0 */
+void b200_vec_scatter_nonneg(b200_float* d_dst, const b200_float* d_src, const int* d_idx, int n);
 
 int  b200_csr_nrows(const b200_csr* M);
 int  b200_csr_ncols(const b200_csr* M);

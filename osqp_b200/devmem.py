@@ -58,6 +58,8 @@ def kernels(precision="f64"):
         "b200_csr_destroy": (None, [vp]),
         "b200_csr_transpose": (vp, [vp, C.POINTER(C.c_void_p)]),
         "b200_veci_gather": (None, [ip, ip, ip, i]),
+        "b200_csr_symmetric_from_triu": (vp, [i, ip, ip, vp, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p)]),
+        "b200_vec_scatter_nonneg": (None, [vp, vp, ip, i]),
         "b200_csr_nrows": (i, [vp]), "b200_csr_ncols": (i, [vp]), "b200_csr_nnz": (i, [vp]),
         "b200_csr_values": (vp, [vp]),
         "b200_csr_download": (i, [vp, ip, ip, vp]),

@@ -292,3 +292,58 @@ def test_device_transpose_declines_over_long_rows(kern):
     h = csr_to_device(k, M)
     assert not k.b200_csr_transpose(h, None)
     k.b200_csr_destroy(h)
+
+
+@pytest.mark.parametrize("n,density,drop_diag", [(200, 0.05, False), (300, 0.02, True), (64, 0.5, True), (500, 0.0, True)])
+def test_device_symmetric_expansion(kern, n, density, drop_diag):
+    """b200_csr_symmetric_from_triu: full symmetric CSR with a structurally full diagonal, expanded on
+    the device from the upper-triangular CSC; both index maps must address the right copies."""
+    k = kern
+    rng = np.random.default_rng(5)
+    M = sp.random(n, n, density=density, format="csc", random_state=9, data_rvs=lambda s: rng.standard_normal(s))
+    U = sp.triu(M + M.T + sp.diags(rng.standard_normal(n)), format="csc")
+    if drop_diag:       # structurally missing diagonal entries get an explicit zero
+        U = U.tolil()
+        for i in range(0, n, 3):
+            U[i, i] = 0.0
+        U = U.tocsc()
+        U.eliminate_zeros()
+    if density == 0.0:
+        U = sp.csc_matrix(([2.0, -1.0, 4.0], ([0, 1, 5], [0, 7, 5])), shape=(n, n))
+    U.sort_indices()
+    p = np.ascontiguousarray(U.indptr, dtype=np.int32)
+    i = np.ascontiguousarray(U.indices, dtype=np.int32)
+    x = np.ascontiguousarray(U.data, dtype=np.float64)
+    mu, ml = C.c_void_p(), C.c_void_p()
+    h = k.b200_csr_symmetric_from_triu(n, p.ctypes.data, i.ctypes.data, x.ctypes.data, C.byref(mu), C.byref(ml))
+    assert h
+    full = (U + sp.triu(U, 1).T).tocsr()
+    # structurally full diagonal: add explicit zeros where missing
+    pattern = (full != 0).astype(np.int8) + sp.eye(n, format="csr", dtype=np.int8)
+    rows, cols = pattern.nonzero()
+    order = np.lexsort((cols, rows))
+    rows, cols = rows[order], cols[order]
+    vals = np.asarray(full[rows, cols]).ravel()
+    rp_ref = np.concatenate([[0], np.cumsum(np.bincount(rows, minlength=n))]).astype(np.int32)
+    nnzf = k.b200_csr_nnz(h)
+    assert nnzf == rows.size
+    rp = np.zeros(n + 1, dtype=np.int32)
+    ci = np.zeros(nnzf, dtype=np.int32)
+    vx = np.zeros(nnzf, dtype=np.float64)
+    assert k.b200_csr_download(h, rp.ctypes.data, ci.ctypes.data, vx.ctypes.data) == 0
+    assert np.array_equal(rp, rp_ref) and np.array_equal(ci, cols) and np.array_equal(vx, vals)
+    hu, hl = np.zeros(U.nnz, dtype=np.int32), np.zeros(U.nnz, dtype=np.int32)
+    assert k.b200_copy_out(hu.ctypes.data, mu, U.nnz * 4) == 0 and k.b200_copy_out(hl.ctypes.data, ml, U.nnz * 4) == 0
+    er, ec = U.tocoo().row, U.tocoo().col          # CSC order (sorted indices): same order as the data
+    Uc = U.tocoo()
+    order_csc = np.lexsort((Uc.row, Uc.col))
+    er, ec, ev = Uc.row[order_csc], Uc.col[order_csc], Uc.data[order_csc]
+    row_of = np.repeat(np.arange(n), np.diff(rp))
+    assert np.array_equal(row_of[hu], er) and np.array_equal(ci[hu], ec) and np.array_equal(vx[hu], ev)
+    off = er != ec
+    assert (hl[~off] == -1).all()
+    assert np.array_equal(row_of[hl[off]], ec[off]) and np.array_equal(ci[hl[off]], er[off])
+    assert np.array_equal(vx[hl[off]], ev[off])
+    k.b200_free(mu)
+    k.b200_free(ml)
+    k.b200_csr_destroy(h)
