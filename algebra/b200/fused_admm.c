@@ -26,6 +26,17 @@ void osqp_ref_update_z(OSQPSolver* solver);
 void osqp_ref_update_y(OSQPSolver* solver);
 void osqp_ref_update_info(OSQPSolver* solver, OSQPInt iter, OSQPInt polishing);
 
+/* A x carried through the relaxation step: valid from the first exact product of a
+ * solve (update_info at iteration 1) until the solve ends; recomputed exactly every
+ * AX_EXACT_EVERY-th check so that rounding drift cannot accumulate.  One record per host thread
+ * (like the library context), keyed by the solver. */
+#define AX_EXACT_EVERY 10
+static _Thread_local struct {
+  const OSQPSolver* solver;
+  int               valid;
+  int               checks;
+} ax_carry;
+
 static int unfused(void) {
   static int v = -1;
   if (v < 0) v = getenv("OSQP_B200_UNFUSED") ? 1 : 0;
@@ -40,6 +51,10 @@ void update_xz_tilde(OSQPSolver* solver, OSQPInt admm_iter) {
   if (unfused()) {
     osqp_ref_update_xz_tilde(solver, admm_iter);
     return;
+  }
+  if (admm_iter == 1 || ax_carry.solver != solver) {   /* new solve: x, A, scaling may all have changed */
+    ax_carry.solver = solver;
+    ax_carry.valid  = 0;
   }
   b200_admm_compute_rhs(work->xtilde_view->d_val, work->ztilde_view->d_val, work->x_prev->d_val,
                         work->data->q->d_val, work->z_prev->d_val, work->y->d_val,
@@ -60,12 +75,14 @@ void update_x(OSQPSolver* solver) {
     osqp_ref_update_x(solver);
     return;
   }
-  b200_admm_update_xzy(work->x->d_val, work->delta_x->d_val, work->z->d_val, work->y->d_val,
-                       work->delta_y->d_val, work->xtilde_view->d_val, work->ztilde_view->d_val,
-                       work->x_prev->d_val, work->z_prev->d_val, work->data->l->d_val,
-                       work->data->u->d_val, vec ? work->rho_vec->d_val : OSQP_NULL,
-                       vec ? work->rho_inv_vec->d_val : OSQP_NULL, settings->rho, work->rho_inv,
-                       settings->alpha, (int)work->data->n, (int)work->data->m);
+  b200_admm_update_xzy_carry(work->x->d_val, work->delta_x->d_val, work->z->d_val, work->y->d_val,
+                             work->delta_y->d_val, work->xtilde_view->d_val, work->ztilde_view->d_val,
+                             work->x_prev->d_val, work->z_prev->d_val, work->data->l->d_val,
+                             work->data->u->d_val, vec ? work->rho_vec->d_val : OSQP_NULL,
+                             vec ? work->rho_inv_vec->d_val : OSQP_NULL, settings->rho, work->rho_inv,
+                             settings->alpha, (int)work->data->n, (int)work->data->m,
+                             (ax_carry.valid && ax_carry.solver == solver && work->data->m > 0)
+                                 ? work->Ax->d_val : OSQP_NULL);
 }
 
 void update_z(OSQPSolver* solver) {
@@ -95,7 +112,15 @@ void update_info(OSQPSolver* solver, OSQPInt iter, OSQPInt polishing) {
   }
   info->iter = iter;
 
-  if (m) OSQPMatrix_Axpy(work->data->A, work->x, work->Ax, 1.0, 0.0);
+  if (m) {
+    /* A x: carried by the fused x/z/y update since the last exact product of this solve */
+    if (!(ax_carry.valid && ax_carry.solver == solver) || ++ax_carry.checks >= AX_EXACT_EVERY ||
+        getenv("B200_NO_AX_CARRY")) {
+      OSQPMatrix_Axpy(work->data->A, work->x, work->Ax, 1.0, 0.0);
+      ax_carry.checks = 0;
+      ax_carry.valid  = (ax_carry.solver == solver) && !getenv("B200_NO_AX_CARRY");
+    }
+  }
   OSQPMatrix_Axpy(work->data->P, work->x, work->Px, 1.0, 0.0);
   if (m) OSQPMatrix_Atxpy(work->data->A, work->y, work->Aty, 1.0, 0.0);
 

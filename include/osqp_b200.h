@@ -229,6 +229,17 @@ void b200_admm_update_xzy(b200_float* d_x, b200_float* d_delta_x, b200_float* d_
                           const b200_float* d_l, const b200_float* d_u,
                           const b200_float* d_rho_vec, const b200_float* d_rho_inv_vec,
                           b200_float rho, b200_float rho_inv, b200_float alpha, int n, int m);
+/* same, and carries A x through the relaxation step when d_Ax != NULL (d_Ax holds A x_prev on
+ * entry, A x on exit: A x+ = alpha z~ + (1 - alpha) A x since z~ = A x~): the termination check
+ * then needs no SpMV for A x (compute_prim_res, src/auxil.c:308-332) */
+void b200_admm_update_xzy_carry(b200_float* d_x, b200_float* d_delta_x, b200_float* d_z,
+                                b200_float* d_y, b200_float* d_delta_y,
+                                const b200_float* d_xtilde, const b200_float* d_ztilde,
+                                const b200_float* d_x_prev, const b200_float* d_z_prev,
+                                const b200_float* d_l, const b200_float* d_u,
+                                const b200_float* d_rho_vec, const b200_float* d_rho_inv_vec,
+                                b200_float rho, b200_float rho_inv, b200_float alpha, int n, int m,
+                                b200_float* d_Ax);
 
 /* All reductions of one termination check in ONE kernel + ONE device->host copy, instead of the
  * ~13 synchronising reductions and ~7 elementwise kernels of update_info / compute_prim_res /

@@ -43,6 +43,10 @@ struct Context {
   char         name[256]  = {0};
   int          trace_on   = 0;   // B200_TRACE_FILE: one CUDA event + host timestamp per launch
   int          slot       = 0;   // index of this context (per-context __constant__ argument blocks)
+  // pinned staging buffers of upload(): allocated at the first large upload, kept until shutdown
+  static constexpr int kStageBufs = 4;
+  void*        h_stage[kStageBufs] = {nullptr, nullptr, nullptr, nullptr};
+  cudaEvent_t  stage_ev[kStageBufs] = {nullptr, nullptr, nullptr, nullptr};
   int          args_valid = 0;   // the constant block of this slot holds the last PcgArgs this thread copied
 };
 
@@ -96,6 +100,12 @@ inline int ew_grid(long long n) {
   if (want < 1) want = 1;
   return (int)(want < cap ? want : cap);
 }
+
+// context.cu: host -> device copy of a (pageable) user array on the library stream.  Large arrays
+// go through pinned staging buffers filled by several host threads (a pageable cudaMemcpyAsync is
+// staged by the driver on one thread at ~10 GB/s: 14 ms for the 137 MB matrix of the Lasso workload);
+// on return the source may be reused, as with a pageable cudaMemcpyAsync.
+bool upload(void* d_dst, const void* h_src, size_t bytes);
 
 // context.cu: wait until the device has posted sequence number `seq` in the mailbox.  Returns
 // false (after synchronising the stream) if the stream finished or failed without posting it.

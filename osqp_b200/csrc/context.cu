@@ -9,6 +9,7 @@
 #include <ctime>
 #include <vector>
 #include <atomic>
+#include <thread>
 
 namespace b200 {
 Context& ctx() {
@@ -45,6 +46,59 @@ double host_now_us() {
   return ts.tv_sec * 1e6 + ts.tv_nsec * 1e-3;
 }
 }  // namespace
+namespace {
+constexpr size_t kStageChunk   = 8u << 20;    // bytes per pinned staging buffer
+constexpr size_t kStageMinSize = 16u << 20;   // smaller uploads: plain (driver-staged) copy
+}  // namespace
+
+bool upload(void* d_dst, const void* h_src, size_t bytes) {
+  Context& c = ctx();
+  if (bytes == 0) return true;
+  static const bool off = getenv("B200_NO_STAGED_UPLOAD") != nullptr;
+  if (bytes < kStageMinSize || off)
+    return check(cudaMemcpyAsync(d_dst, h_src, bytes, cudaMemcpyHostToDevice, c.stream), "upload");
+  for (int b = 0; b < Context::kStageBufs; b++) {
+    if (!c.h_stage[b]) {
+      if (cudaHostAlloc(&c.h_stage[b], kStageChunk, cudaHostAllocDefault) != cudaSuccess ||
+          cudaEventCreateWithFlags(&c.stage_ev[b], cudaEventDisableTiming) != cudaSuccess) {
+        cudaGetLastError();
+        c.h_stage[b] = nullptr;
+        return check(cudaMemcpyAsync(d_dst, h_src, bytes, cudaMemcpyHostToDevice, c.stream), "upload");
+      }
+    }
+  }
+  // worker b owns buffer b and the chunks b, b + kStageBufs, ...: wait until the previous copy out
+  // of its buffer is done, refill it, enqueue the next copy (the stream serialises the copies; their
+  // destinations are disjoint, so their order does not matter)
+  const size_t nchunks = (bytes + kStageChunk - 1) / kStageChunk;
+  std::atomic<int> failed{0};
+  const int device = c.device;
+  cudaStream_t st = c.stream;
+  void* const* stage = c.h_stage;
+  cudaEvent_t const* ev = c.stage_ev;
+  auto work = [&](int b) {
+    if (cudaSetDevice(device) != cudaSuccess) { failed = 1; return; }
+    bool used = false;
+    for (size_t ch = (size_t)b; ch < nchunks; ch += Context::kStageBufs) {
+      const size_t o = ch * kStageChunk, len = (bytes - o < kStageChunk) ? bytes - o : kStageChunk;
+      if (used && cudaEventSynchronize(ev[b]) != cudaSuccess) { failed = 1; return; }
+      memcpy(stage[b], (const char*)h_src + o, len);
+      if (cudaMemcpyAsync((char*)d_dst + o, stage[b], len, cudaMemcpyHostToDevice, st) != cudaSuccess ||
+          cudaEventRecord(ev[b], st) != cudaSuccess) { failed = 1; return; }
+      used = true;
+    }
+  };
+  std::thread th[Context::kStageBufs];
+  for (int b = 1; b < Context::kStageBufs; b++) th[b] = std::thread(work, b);
+  work(0);
+  for (int b = 1; b < Context::kStageBufs; b++) th[b].join();
+  // the buffers are reused by the next upload: make sure the last copies have left them
+  for (int b = 0; b < Context::kStageBufs; b++)
+    if ((size_t)b < nchunks && cudaEventSynchronize(ev[b]) != cudaSuccess) failed = 1;
+  if (failed) return check(cudaErrorUnknown, "staged upload");
+  return true;
+}
+
 bool mail_wait(unsigned long long seq) {
   Context& c = ctx();
   volatile unsigned long long* word = reinterpret_cast<volatile unsigned long long*>(c.h_mail + kMailSlots);
@@ -172,6 +226,12 @@ void b200_shutdown(void) {
   cudaFreeHost(c.h_scalar);
   cudaFreeHost(c.h_mail);
   c.h_mail = c.d_mail = nullptr;
+  for (int b = 0; b < Context::kStageBufs; b++) {
+    if (c.h_stage[b]) cudaFreeHost(c.h_stage[b]);
+    if (c.stage_ev[b]) cudaEventDestroy(c.stage_ev[b]);
+    c.h_stage[b] = nullptr;
+    c.stage_ev[b] = nullptr;
+  }
   cudaStreamDestroy(c.stream);
   slot_release(c.slot);
   c.d_partials = nullptr;
@@ -261,7 +321,7 @@ int b200_copy_in(void* d_dst, const void* src, size_t bytes) {
   }
   // pageable host memory: cudaMemcpyAsync stages it before returning, so the caller may
   // reuse `src` immediately; ordering with earlier kernels is kept by the stream
-  return B200_CHECK(cudaMemcpyAsync(d_dst, src, bytes, cudaMemcpyHostToDevice, c.stream)) ? 0 : 1;
+  return upload(d_dst, src, bytes) ? 0 : 1;
 }
 
 int b200_copy_out(void* dst, const void* d_src, size_t bytes) {

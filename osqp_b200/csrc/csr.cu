@@ -201,13 +201,10 @@ b200_csr* b200_csr_create(int nrows, int ncols, int nnz, const int* h_row_ptr, c
   ok &= B200_CHECK(dev_malloc(&M->d_col_ind, sizeof(int) * ((size_t)nnz + 2 * kPad)));
   ok &= B200_CHECK(dev_malloc(&M->d_val, sizeof(T) * ((size_t)nnz + 2 * kPad)));
   if (!ok) { b200_csr_destroy(M); return nullptr; }
-  ok &= B200_CHECK(cudaMemcpyAsync(M->d_row_ptr, h_row_ptr, sizeof(int) * ((size_t)nrows + 1),
-                                   cudaMemcpyHostToDevice, c.stream));
+  ok &= upload(M->d_row_ptr, h_row_ptr, sizeof(int) * ((size_t)nrows + 1));
   if (nnz > 0) {
-    ok &= B200_CHECK(cudaMemcpyAsync(M->d_col_ind, h_col_ind, sizeof(int) * (size_t)nnz,
-                                     cudaMemcpyHostToDevice, c.stream));
-    ok &= B200_CHECK(cudaMemcpyAsync(M->d_val, h_val, sizeof(T) * (size_t)nnz,
-                                     cudaMemcpyHostToDevice, c.stream));
+    ok &= upload(M->d_col_ind, h_col_ind, sizeof(int) * (size_t)nnz);
+    ok &= upload(M->d_val, h_val, sizeof(T) * (size_t)nnz);
   }
   if (!ok || b200_build_schedule(M, h_row_ptr) != 0) { b200_csr_destroy(M); return nullptr; }
   return M;

@@ -376,9 +376,9 @@ b200_csr* b200_csr_symmetric_from_triu(int n, const int* h_p, const int* h_i, co
   ok &= B200_CHECK(dev_malloc(&mu, sizeof(int) * ((size_t)nnz + 1)));
   ok &= B200_CHECK(dev_malloc(&ml, sizeof(int) * ((size_t)nnz + 1)));
   if (ok) {
-    ok &= B200_CHECK(cudaMemcpyAsync(rpL, h_p, sizeof(int) * ((size_t)n + 1), cudaMemcpyHostToDevice, st));
-    ok &= B200_CHECK(cudaMemcpyAsync(ciL, h_i, sizeof(int) * (size_t)nnz, cudaMemcpyHostToDevice, st));
-    ok &= B200_CHECK(cudaMemcpyAsync(vL, h_x, sizeof(T) * (size_t)nnz, cudaMemcpyHostToDevice, st));
+    ok &= upload(rpL, h_p, sizeof(int) * ((size_t)n + 1));
+    ok &= upload(ciL, h_i, sizeof(int) * (size_t)nnz);
+    ok &= upload(vL, h_x, sizeof(T) * (size_t)nnz);
   }
   if (ok) U = transpose_impl(rpL, ciL, vL, n, n, nnz, false, &tmap);
   if (ok && U) {

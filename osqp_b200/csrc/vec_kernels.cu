@@ -450,9 +450,24 @@ void b200_admm_compute_rhs(T* xt, T* zt, const T* x_prev, const T* q, const T* z
 //   z  = clip(alpha z~ + (1-alpha) z_prev + y/rho, l, u)
 //   dy = rho (alpha z~ + (1-alpha) z_prev - z) ;    y += dy
 // expression order follows the reference's add_scaled / add_scaled3 calls.
+void b200_admm_update_xzy_carry(T* x, T* dx, T* z, T* y, T* dy, const T* xt, const T* zt, const T* x_prev,
+                                const T* z_prev, const T* l, const T* u, const T* rho_vec,
+                                const T* rho_inv_vec, T rho, T rho_inv, T alpha, int n, int m, T* Ax);
+
 void b200_admm_update_xzy(T* x, T* dx, T* z, T* y, T* dy, const T* xt, const T* zt, const T* x_prev,
                           const T* z_prev, const T* l, const T* u, const T* rho_vec,
                           const T* rho_inv_vec, T rho, T rho_inv, T alpha, int n, int m) {
+  b200_admm_update_xzy_carry(x, dx, z, y, dy, xt, zt, x_prev, z_prev, l, u, rho_vec, rho_inv_vec, rho, rho_inv,
+                             alpha, n, m, nullptr);
+}
+
+// Same, and additionally carries the product A x through the relaxation step when Ax != NULL:
+// x+ = alpha x~ + (1 - alpha) x  and  z~ = A x~ (what the linear solve returns), so
+// A x+ = alpha z~ + (1 - alpha) A x  -- the termination check then needs no SpMV for A x
+// (SURVEY.md section 8f.1).  Ax must hold A x_prev on entry.
+void b200_admm_update_xzy_carry(T* x, T* dx, T* z, T* y, T* dy, const T* xt, const T* zt, const T* x_prev,
+                                const T* z_prev, const T* l, const T* u, const T* rho_vec,
+                                const T* rho_inv_vec, T rho, T rho_inv, T alpha, int n, int m, T* Ax) {
   const int tot = n + m;
   const T oma = (T)1.0 - alpha;
   launch_ew(tot, [=] __device__(int i) {
@@ -479,6 +494,7 @@ void b200_admm_update_xzy(T* x, T* dx, T* z, T* y, T* dy, const T* xt, const T* 
       z[j]  = zn;
       dy[j] = d;
       y[j]  = yj + d;
+      if (Ax) Ax[j] = alpha * zti + oma * Ax[j];
     }
   });
 }

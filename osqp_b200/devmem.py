@@ -81,6 +81,7 @@ def kernels(precision="f64"):
                                   C.POINTER(C.c_int), C.POINTER(C.c_double), C.POINTER(C.c_double)]),
         "b200_admm_compute_rhs": (None, [vp, vp, vp, vp, vp, vp, vp, F, F, i, i]),
         "b200_admm_update_xzy": (None, [vp] * 13 + [F, F, F, i, i]),
+        "b200_admm_update_xzy_carry": (None, [vp] * 13 + [F, F, F, i, i, vp]),
         "b200_admm_residuals": (None, [vp] * 11 + [F, F, i, i, vp]),
         "b200_epoch": (C.c_ulonglong, []),
     }
