@@ -67,7 +67,7 @@ def shard_problem(pb, rank, world):
 # nonzeros (and its couplings in P) live there, and SHARED otherwise.  Each rank solves over
 # [shared columns ; its local columns]: only the shared slice is ever exchanged.
 
-def plan_column_split(P, A, world, max_link_degree=3):
+def plan_column_split(P, A, world, max_link_degree=3, Acsr=None):
     """Returns a dict with, per rank r: rows[r] (global row ids), cols[r] = shared ++ local_r (global
     column ids), and `shared` (global ids of the shared columns, identical leading part of cols[r])."""
     A = sp.csc_matrix(A)
@@ -97,7 +97,8 @@ def plan_column_split(P, A, world, max_link_degree=3):
     first[comp[o[starts_c]]] = o[starts_c]
     root = first[comp]
     # 2. clusters -> ranks, greedy in order of first row, balanced by nonzeros (+1 per row)
-    Acsr = A.tocsr()
+    if Acsr is None:                 # callers that also shard pass the CSR copy they already made
+        Acsr = A.tocsr()
     w_row = np.diff(Acsr.indptr).astype(np.int64) + 1
     order = np.argsort(root, kind="stable")                 # rows grouped by cluster, clusters by first row
     w_sorted = w_row[order]
@@ -146,11 +147,11 @@ def plan_column_split(P, A, world, max_link_degree=3):
     return dict(shared=shared, rows=rows, cols=cols, n=n, m=m, world=world)
 
 
-def shard_problem_split(pb, rank, plan):
+def shard_problem_split(pb, rank, plan, Acsr=None):
     """Rank `rank`'s QP under a column-split plan.  A row with no entries and infinite bounds is
     appended when the local problem would otherwise have as many rows as columns (the backend
     tells row vectors from column vectors by their length)."""
-    A = sp.csr_matrix(pb["A"])
+    A = Acsr if Acsr is not None else sp.csr_matrix(pb["A"])
     P = sp.csc_matrix(pb["P"])
     R, Cc = plan["rows"][rank], plan["cols"][rank]
     A_r = A[R][:, Cc].tocsc()
@@ -242,8 +243,10 @@ class ShardedOSQP(OSQP):
         pb = dict(P=P, q=q, A=A, l=l, u=u)
         self.n_global, self.m_global = sp.csc_matrix(P).shape[0], sp.csc_matrix(A).shape[0]
         if self.layout == "split":
-            self.plan = plan_column_split(P, A, self.world)
-            sh = shard_problem_split(pb, self.rank, self.plan)
+            Acsr = sp.csr_matrix(A)          # one CSC -> CSR conversion shared by the planner and the slicer
+            self.plan = plan_column_split(P, A, self.world, Acsr=Acsr)
+            sh = shard_problem_split(pb, self.rank, self.plan, Acsr=Acsr)
+            del Acsr
             self.padded = sh["padded"]
             self.n_shared = sh["n_shared"]
             rc = self._lib.osqp_b200_dist_configure_split(sh["A"].shape[1], sh["A"].shape[0], self.n_shared,
