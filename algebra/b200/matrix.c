@@ -4,11 +4,16 @@
  * Implements /root/reference/include/private/algebra_matrix.h:26-138.  Numerical contract =
  * CPU reference (algebra/builtin/matrix.c, algebra/_common/csc_math.c); storage design takes
  * over the role of algebra/cuda/matrix.cu:32-172 + src/cuda_csr.cu:489-714 (CSR of A, stored
- * transpose, full symmetric P with guaranteed diagonal, index maps for value updates) but the
- * format conversions are plain counting sorts on the host instead of cuSPARSE/thrust calls:
- *   - the user's CSC of A *is* the CSR of A' -> no work, identity value map;
- *   - CSR of A = one counting sort by row, recording where every CSC entry lands;
- *   - full P = lower mirror + upper copy of the triu CSC, diagonal inserted where missing.
+ * transpose, full symmetric P with guaranteed diagonal, index maps for value updates) without
+ * cuSPARSE/thrust:
+ *   - the user's CSC of A *is* the CSR of A' -> one upload, identity value map;
+ *   - CSR of A = transpose of that copy ON THE DEVICE (osqp_b200/csrc/transpose.cu: count, scan,
+ *     scatter, per-row rank sort), index map kept in HBM;
+ *   - full P = lower mirror + upper copy of the triu CSC, diagonal inserted where missing, also
+ *     expanded on the device (b200_csr_symmetric_from_triu).
+ * The host builders below (a parallel stable counting sort and a serial symmetric expansion) are
+ * the fall-back for matrices with rows longer than the device rank-sort limit and for
+ * B200_HOST_TRANSPOSE=1; both paths produce bit-identical matrices.
  */
 #include "osqp.h"
 #include "algebra_matrix.h"
@@ -35,9 +40,8 @@ static int trace_on(void) {
 
 /* ------------------------------------------------------------------ builders */
 
-/* ---- parallel stable counting sort (CSC -> CSR) ------------------------------------------
- * The transpose of a 1e7..1e8-entry matrix is the dominant cost of osqp_setup when done by one
- * core (205 of 270 ms for the 1.14e7-nnz Lasso, measured), so it is split over host threads:
+/* ---- fall-back: parallel stable counting sort (CSC -> CSR) on the host ------------------------
+ * One core needs 205 ms for the 1.14e7-nnz Lasso (measured), so the sort is split over host threads:
  * thread t owns a contiguous chunk of COLUMNS; (1) it histograms the rows of its chunk,
  * (2) row offsets are the prefix sum over rows of the summed histograms, and every thread's
  * private cursor for row i starts after the entries of the threads before it, (3) it scatters its
