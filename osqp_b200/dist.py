@@ -15,18 +15,20 @@ from . import OSQP
 from .devmem import kernels
 
 
-def partition_rows(A, world, n=None):
+def partition_rows(A, world, n=None, row_nnz=None):
     """Contiguous row blocks balanced by nonzeros (+1 per row for the vector work).
     Returns the world+1 row boundaries.  No block may have exactly n rows (the backend tells
-    row-sharded vectors from replicated ones by their length), and none may be empty."""
-    A = sp.csr_matrix(A)
+    row-sharded vectors from replicated ones by their length), and none may be empty.
+    `row_nnz` (entries per row) spares the CSR conversion when the caller already has it."""
     m = A.shape[0]
     n = A.shape[1] if n is None else n
     if world <= 1:
         return np.array([0, m], dtype=np.int64)
     if m < world:
         raise ValueError("fewer rows than ranks")
-    w = np.diff(A.indptr).astype(np.int64) + 1
+    if row_nnz is None:
+        row_nnz = np.diff(sp.csr_matrix(A).indptr)
+    w = np.asarray(row_nnz).astype(np.int64) + 1
     cum = np.concatenate([[0], np.cumsum(w)])
     bounds = [0]
     for r in range(1, world):
@@ -67,7 +69,7 @@ def shard_problem(pb, rank, world):
 # nonzeros (and its couplings in P) live there, and SHARED otherwise.  Each rank solves over
 # [shared columns ; its local columns]: only the shared slice is ever exchanged.
 
-def plan_column_split(P, A, world, max_link_degree=3, Acsr=None):
+def plan_column_split(P, A, world, max_link_degree=3):
     """Returns a dict with, per rank r: rows[r] (global row ids), cols[r] = shared ++ local_r (global
     column ids), and `shared` (global ids of the shared columns, identical leading part of cols[r])."""
     A = sp.csc_matrix(A)
@@ -97,9 +99,9 @@ def plan_column_split(P, A, world, max_link_degree=3, Acsr=None):
     first[comp[o[starts_c]]] = o[starts_c]
     root = first[comp]
     # 2. clusters -> ranks, greedy in order of first row, balanced by nonzeros (+1 per row)
-    if Acsr is None:                 # callers that also shard pass the CSR copy they already made
-        Acsr = A.tocsr()
-    w_row = np.diff(Acsr.indptr).astype(np.int64) + 1
+    # entries per row straight from the CSC row indices: the planner never needs a CSR copy
+    row_nnz = np.bincount(A.indices, minlength=m)
+    w_row = row_nnz.astype(np.int64) + 1
     order = np.argsort(root, kind="stable")                 # rows grouped by cluster, clusters by first row
     w_sorted = w_row[order]
     cum = np.cumsum(w_sorted)
@@ -136,25 +138,30 @@ def plan_column_split(P, A, world, max_link_degree=3, Acsr=None):
     # local, fall back to plain contiguous row blocks with every column shared
     cnt = np.bincount(rank_of_row, weights=w_row, minlength=world)
     if cnt.min() == 0 or cnt.max() > 2.0 * cnt.mean() or shared.size > 0.5 * n:
-        bounds = partition_rows(Acsr, world, n=-1)
+        bounds = partition_rows(A, world, n=-1, row_nnz=row_nnz)
         rank_of_row = np.repeat(np.arange(world), np.diff(bounds))
         owner[:] = -1
         shared = np.arange(n)
     rows, cols = [], []
+    row_local = np.empty(m, dtype=np.int64)          # position of a row inside its rank's block
     for r in range(world):
         rows.append(np.nonzero(rank_of_row == r)[0])
+        row_local[rows[r]] = np.arange(rows[r].size)
         cols.append(np.concatenate([shared, np.nonzero(owner == r)[0]]))
-    return dict(shared=shared, rows=rows, cols=cols, n=n, m=m, world=world)
+    return dict(shared=shared, rows=rows, cols=cols, n=n, m=m, world=world, rank_of_row=rank_of_row,
+                row_local=row_local)
 
 
 def shard_problem_split(pb, rank, plan, Acsr=None):
     """Rank `rank`'s QP under a column-split plan.  A row with no entries and infinite bounds is
     appended when the local problem would otherwise have as many rows as columns (the backend
     tells row vectors from column vectors by their length)."""
-    A = Acsr if Acsr is not None else sp.csr_matrix(pb["A"])
     P = sp.csc_matrix(pb["P"])
     R, Cc = plan["rows"][rank], plan["cols"][rank]
-    A_r = A[R][:, Cc].tocsc()
+    if Acsr is not None:
+        A_r = Acsr[R][:, Cc].tocsc()
+    else:
+        A_r = _slice_csc(pb["A"], R.size, Cc, plan["rank_of_row"], plan["row_local"], rank)
     P_r = sp.triu(P[Cc][:, Cc], format="csc")
     l, u = np.asarray(pb["l"], dtype=float)[R], np.asarray(pb["u"], dtype=float)[R]
     padded = 0
@@ -164,6 +171,29 @@ def shard_problem_split(pb, rank, plan, Acsr=None):
         padded = 1
     return dict(P=P_r, q=np.asarray(pb["q"], dtype=float)[Cc], A=A_r, l=l, u=u, padded=padded,
                 n_shared=int(plan["shared"].size))
+
+
+def _slice_csc(A, n_rows_local, cols, rank_of_row, row_local, rank):
+    """A[rows of `rank`][:, cols] as CSC without any format conversion: gather the selected columns'
+    segments, keep the entries whose row lives on `rank`, renumber the rows.  Row order inside a
+    column is preserved (row_local is increasing in the global row id), so sorted input gives sorted
+    output -- identical to scipy's A.tocsr()[rows][:, cols].tocsc()."""
+    A = A if sp.isspmatrix_csc(A) else sp.csc_matrix(A)
+    A.sort_indices()
+    lengths = (A.indptr[cols + 1] - A.indptr[cols]).astype(np.int64)
+    total = int(lengths.sum())
+    starts = A.indptr[cols].astype(np.int64)
+    # positions of the selected entries in A.indices / A.data, column after column
+    offs = np.concatenate([[0], np.cumsum(lengths)])[:-1]
+    idx = np.repeat(starts - offs, lengths) + np.arange(total, dtype=np.int64)
+    rows_g = A.indices[idx]
+    keep = rank_of_row[rows_g] == rank
+    col_id = np.repeat(np.arange(cols.size, dtype=np.int64), lengths)[keep]
+    indptr = np.concatenate([[0], np.cumsum(np.bincount(col_id, minlength=cols.size))])
+    out = sp.csc_matrix((A.data[idx][keep], row_local[rows_g[keep]].astype(np.int32), indptr.astype(np.int32)),
+                        shape=(n_rows_local, cols.size))
+    out.has_sorted_indices = True
+    return out
 
 
 def assemble_solution(parts, n_global, m_global, plan=None, bounds=None):
@@ -243,10 +273,9 @@ class ShardedOSQP(OSQP):
         pb = dict(P=P, q=q, A=A, l=l, u=u)
         self.n_global, self.m_global = sp.csc_matrix(P).shape[0], sp.csc_matrix(A).shape[0]
         if self.layout == "split":
-            Acsr = sp.csr_matrix(A)          # one CSC -> CSR conversion shared by the planner and the slicer
-            self.plan = plan_column_split(P, A, self.world, Acsr=Acsr)
-            sh = shard_problem_split(pb, self.rank, self.plan, Acsr=Acsr)
-            del Acsr
+            # planner and slicer work on the CSC arrays directly: no CSC -> CSR conversion
+            self.plan = plan_column_split(P, A, self.world)
+            sh = shard_problem_split(pb, self.rank, self.plan)
             self.padded = sh["padded"]
             self.n_shared = sh["n_shared"]
             rc = self._lib.osqp_b200_dist_configure_split(sh["A"].shape[1], sh["A"].shape[0], self.n_shared,
