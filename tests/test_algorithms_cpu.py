@@ -139,3 +139,77 @@ def test_carried_Ax_follows_the_relaxation_step():
         x = alpha * xt + (1 - alpha) * x
         Ax = alpha * zt + (1 - alpha) * Ax
     assert np.abs(Ax - A @ x).max() <= 1e-12 * max(1.0, np.abs(Ax).max())
+
+
+def test_column_split_cg_equals_the_global_cg():
+    """The row-sharded CG of pcg_graph.cu (b200_pcg_sharded_solve) emulated with numpy for 3 virtual
+    ranks: every rank applies (P + sigma I) only to the columns it counts (rank 0: shared + own, the
+    others: own) plus A_r' rho A_r, the SHARED head of the partial is summed over the ranks, and the
+    dots are summed over [shared once ; every rank's own columns].  Must reproduce the CG on the whole
+    KKT operator iterate for iterate."""
+    from osqp_b200 import problems
+    from osqp_b200.dist import plan_column_split, shard_problem_split, assemble_solution
+    world, sigma = 3, 1e-6
+    pb = problems.huber(12, 240, density=0.2, seed=8)
+    A = sp.csr_matrix(pb["A"])
+    P = sp.csc_matrix(pb["P"])
+    Pfull = (sp.triu(P) + sp.triu(P, 1).T).tocsr()
+    m, n = A.shape
+    rng = np.random.default_rng(8)
+    rho_g = rng.uniform(0.1, 1.0, m)
+    b_g = rng.standard_normal(n)
+    K = (Pfull + sigma * sp.eye(n) + A.T @ sp.diags(rho_g) @ A).tocsr()
+    minv_g = 1.0 / K.diagonal()
+    x_ref, it_ref, hist_ref = _pcg_three_dots(K, b_g, minv_g, np.zeros(n), 1e-10, 60)
+
+    plan = plan_column_split(P, A, world)
+    ns = plan["shared"].size
+    assert 0 < ns < n
+    ranks = []
+    for r in range(world):
+        sh = shard_problem_split(pb, r, plan)
+        cols, rows = plan["cols"][r], plan["rows"][r]
+        Ar = sp.csr_matrix(sh["A"])[:len(rows)]
+        Pr = sp.csc_matrix(sh["P"])
+        Pr = (sp.triu(Pr) + sp.triu(Pr, 1).T).tocsr()
+        counted = np.ones(cols.size, dtype=bool)
+        if r > 0:
+            counted[:ns] = False                    # shared columns: P + sigma I carried by rank 0 only
+        ranks.append(dict(A=Ar, P=Pr, rho=rho_g[rows], cols=cols, counted=counted, b=b_g[cols],
+                          minv=minv_g[cols], x=np.zeros(cols.size)))
+
+    def apply_K(vecs):
+        parts = []
+        for rk, v in zip(ranks, vecs):
+            kp = rk["A"].T @ (rk["rho"] * (rk["A"] @ v))
+            kp += np.where(rk["counted"], rk["P"] @ v + sigma * v, 0.0)
+            parts.append(kp)
+        head = sum(p[:ns] for p in parts)           # the ONE vector exchange: all-reduce of the shared head
+        for p in parts:
+            p[:ns] = head
+        return parts
+
+    def dot(us, vs):                                # shared slice once (rank 0) + every rank's own columns
+        return sum(float(u[(0 if i == 0 else ns):] @ v[(0 if i == 0 else ns):]) for i, (u, v) in enumerate(zip(us, vs)))
+
+    xs = [rk["x"] for rk in ranks]
+    rs = [kp - rk["b"] for kp, rk in zip(apply_K(xs), ranks)]
+    ps = [-(rk["minv"] * r) for rk, r in zip(ranks, rs)]
+    rTy = dot(rs, [rk["minv"] * r for rk, r in zip(ranks, rs)])
+    for it in range(it_ref):
+        Kps = apply_K(ps)
+        yk = [rk["minv"] * kp for rk, kp in zip(ranks, Kps)]
+        pKp, rkp, kpkp = dot(ps, Kps), dot(rs, yk), dot(Kps, yk)
+        alpha = rTy / pKp
+        beta = max((rTy + alpha * (2 * rkp + alpha * kpkp)) / rTy, 0.0)
+        xs = [x + alpha * p for x, p in zip(xs, ps)]
+        rs = [r + alpha * kp for r, kp in zip(rs, Kps)]
+        ys = [rk["minv"] * r for rk, r in zip(ranks, rs)]
+        ps = [beta * p - y for p, y in zip(ps, ys)]
+        rTy = dot(rs, ys)
+        xg, _ = assemble_solution([(x, np.zeros(len(plan["rows"][i]))) for i, x in enumerate(xs)], n, m, plan=plan)
+        # same iterates; summation orders differ, and CG amplifies rounding slowly with the iteration count
+        tol = (1e-11 if it < 10 else 1e-6) * max(1.0, np.abs(hist_ref[it + 1]).max())
+        assert np.abs(xg - hist_ref[it + 1]).max() <= tol
+        for x in xs[1:]:                            # the replicated slice stays identical on every rank
+            assert np.array_equal(x[:ns], xs[0][:ns])
