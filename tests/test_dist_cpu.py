@@ -209,3 +209,23 @@ def test_csc_native_slicer_equals_scipy_slicing(family, world):
         for key in ("q", "l", "u"):
             assert np.array_equal(fast[key], ref[key])
         assert fast["padded"] == ref["padded"] and fast["n_shared"] == ref["n_shared"]
+
+
+def test_bench_reference_arm_line_contract():
+    """`bench.py --impl reference` (the reference's CPU path timed on the host cores): ONE JSON line on
+    stdout with the keys the driver reads, same metric / unit as the B200 arm."""
+    import json
+    out = subprocess.run([sys.executable, str(ROOT / "bench.py"), "--impl", "reference", "--steps", "1",
+                          "--warmup", "1"], capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [l for l in out.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["metric"] == "admm_iters_per_sec" and d["unit"] == "iter/s"
+    assert d["higher_is_better"] is True and d["n_gpus"] == 1 and d["steps"] == 1 and d["warmup"] == 1
+    assert d["value"] > 0 and d["ms_per_step"] > 0 and d["vs_baseline"] is None
+    assert d["cpu_baseline"]["kind"] == "reference" and d["cpu_baseline"]["cores"] == 1
+    assert d["cpu_baseline"]["value"] == d["value"]
+    assert d["e2e"]["value"] == d["value"] and d["e2e"]["unit"] == d["unit"]
+    assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
+    assert "workload" in d["config"]
