@@ -4,18 +4,24 @@
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
 
 metric : ADMM iterations / second (whole job) at eps_abs = eps_rel = 1e-3, plus time-to-solution.
-workload (N = 1): BASELINE.json configs[1] -- Lasso, 1e5 features x 1e6 samples (~1.14e7 nnz,
-          n = m = 1.2e6), single B200, indirect (PCG) solver, f64.
 step   : one complete osqp_solve of the workload from a cold start.
 value  : iterations / s with the problem resident in HBM (solver set up before the timed region).
 e2e    : the same metric through the public API from HOST arrays: every step is osqp_setup
          (host -> device copies of P, A, q, l, u and all format conversions) + osqp_solve + the
          device -> host read of the solution, on the host clock.
-N > 1  : the path shards as independent QPs (BASELINE configs[4] style): every rank sets up and solves
-         its own instance with no data-path collective -> "scaling": "weak".
-         `--mode sharded` instead solves ONE QP with the rows of A split over the ranks (strong).
+
+plain `python bench.py` (N = 1): BASELINE.json configs[1] -- Lasso, 1e5 features x 1e6 samples (~1.14e7
+         nnz, n = m = 1.2e6), single B200, indirect (PCG) solver, f64.  The line also carries
+         `ref_cuda` (the reference's own algebra/cuda build on the same GPU, same problem and settings),
+         `cpu_baseline` (the CPU oracle on a bounded sample + a parity check of the B200 answer against
+         it) and `cpu_baseline_same_config` (BASELINE configs[0], the designated CPU config, on both).
+under torchrun (any N):  ONE QP of BASELINE configs[3] size -- SVM, 1e7 samples x 1e4 features, 1.2e8 nnz --
+         with the rows of A split over the N ranks (column-split layout, peer-memory exchange inside the
+         CG loop): "scaling": "strong".  Every rank generates only its own sample blocks.  Rank 0 also
+         solves the WHOLE QP on its own GPU in the same run (`strong_scaling`), so the speed-up is
+         measured, not inferred.  `--mode batch` runs N independent QPs instead (configs[4] style, weak).
 --impl reference : the reference's own CPU path (unmodified core + builtin backend + QDLDL
-         restatement = oracle/_ref/libosqp_builtin.so) on a bounded sample of the same generator.
+         restatement = oracle/_ref/libosqp_builtin.so) on a bounded sample of the arm's generator.
 """
 import argparse
 import ctypes
@@ -34,8 +40,9 @@ sys.path.insert(0, str(ROOT))
 
 SETTINGS = dict(eps_abs=1e-3, eps_rel=1e-3, rho_is_vec=0, adaptive_rho_tolerance=2.0,
                 check_termination=5, polishing=0, verbose=0, warm_starting=0)
-CPU_SAMPLE_SCALE = 0.02          # QDLDL fill grows ~ scale^3: 0.02 -> ~6 s, 0.04 -> ~48 s per solve
+CPU_SAMPLE_SCALE = 0.02          # QDLDL fill grows ~ scale^3: 0.02 -> ~2-4 s, 0.04 -> ~24 s per solve
 F = 8
+SHARDED_DEFAULT = dict(workload="svm", n_features=10_000, n_samples=10_000_000, density=1e-3)
 
 
 def make_problem(scale, seed, workload="lasso"):
@@ -53,10 +60,40 @@ def make_problem(scale, seed, workload="lasso"):
     if workload == "svm":          # configs[3]
         return problems.svm(10_000, int(1e7 * scale), density=1e-3, seed=seed)
     if workload == "random_qp":    # configs[0]
-        return problems.random_qp(10_000, 20_000, 200_000, seed=seed)
+        return problems.random_qp(int(10_000 * scale), int(20_000 * scale), int(200_000 * scale), seed=seed)
     if workload == "mpc":          # configs[4], one instance
         return problems.mpc(N=12, seed=seed)
     raise ValueError(workload)
+
+
+def make_shard(rank, world, workload, scale, seed=1):
+    """This rank's part of the sharded workload (block-seeded generators: the global QP is the same for
+    every world size and no rank builds more than its own samples)."""
+    from osqp_b200 import problems
+    kw = dict(n_features=SHARDED_DEFAULT["n_features"], n_samples=int(SHARDED_DEFAULT["n_samples"] * scale),
+              density=SHARDED_DEFAULT["density"], seed=seed)
+    if workload == "svm":
+        return problems.svm_shard(rank, world, **kw)
+    if workload == "huber":
+        return problems.huber_shard(rank, world, **kw)
+    raise ValueError(f"no block-seeded generator for {workload!r} (svm, huber)")
+
+
+def cpu_sample_problem(workload):
+    """bounded sample of the arm's workload for the CPU reference (QDLDL must fit in seconds)"""
+    from osqp_b200 import problems
+    if workload == "lasso":
+        pb = make_problem(CPU_SAMPLE_SCALE, seed=1)
+        return pb, (f"Lasso generator at scale {CPU_SAMPLE_SCALE}: n={pb['P'].shape[0]}, m={pb['A'].shape[0]}, "
+                    f"nnz(A)={pb['A'].nnz}; the full-size KKT factor does not fit QDLDL (fill ~ n_features^2)")
+    if workload in ("svm", "huber"):
+        gen = problems.svm_shard if workload == "svm" else problems.huber_shard
+        pb = gen(0, 1, n_features=300, n_samples=60_000, density=2e-2, seed=1)
+        return pb, (f"{workload} block generator at 300 features x 60000 samples, density 0.02: "
+                    f"n={pb['P'].shape[0]}, m={pb['A'].shape[0]}, nnz(A)={pb['A'].nnz}; at 1e4 features the KKT "
+                    "factor holds a dense 1e4 x 1e4 block (minutes per factorisation)")
+    pb = make_problem(1.0 if workload in ("mpc",) else 0.3, seed=1, workload=workload)
+    return pb, f"{workload} generator, reduced: n={pb['P'].shape[0]}, m={pb['A'].shape[0]}, nnz(A)={pb['A'].nnz}"
 
 
 def peaks():
@@ -104,7 +141,9 @@ class ClockSampler:
                         reasons.add(nm)
             except (ValueError, IndexError):
                 continue
-        return {"sm_mhz": float(np.median(sm)) if sm else None,
+        # median over the samples taken under load (an idle GPU parks its clocks)
+        busy = [c for c in sm if smax and c >= 0.5 * max(smax)] or sm
+        return {"sm_mhz": float(np.median(busy)) if busy else None,
                 "sm_max_mhz": max(smax) if smax else None, "reasons": sorted(reasons),
                 "samples": len(sm)}
 
@@ -114,6 +153,19 @@ def dist_env():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     return rank, world, local
+
+
+def under_torchrun():
+    return "RANK" in os.environ and "WORLD_SIZE" in os.environ
+
+
+def arm_workload(args):
+    """(mode, workload) of this invocation -- shared by both arms so that they name the same config"""
+    mode = args.mode
+    if mode == "auto":
+        mode = "sharded" if under_torchrun() else "single"
+    wl = args.workload or (SHARDED_DEFAULT["workload"] if mode == "sharded" else "lasso")
+    return mode, wl
 
 
 # ------------------------------------------------------------------------ reference (CPU) arm
@@ -128,48 +180,46 @@ def oracle_library():
     return LoadedLibrary(lib)
 
 
-def cpu_step(lib, pb):
-    """one end-to-end step on the CPU path: osqp_setup + osqp_solve; returns (iters, seconds,
-    solve-only seconds)."""
+def cpu_step(lib, pb, **extra):
+    """one end-to-end step on the CPU path: osqp_setup + osqp_solve; returns (result, seconds)."""
     from osqp_b200.interface import OSQP
     t0 = time.perf_counter()
-    s = OSQP(lib).setup(pb["P"], pb["q"], pb["A"], pb["l"], pb["u"], **SETTINGS)
+    s = OSQP(lib).setup(pb["P"], pb["q"], pb["A"], pb["l"], pb["u"], **dict(SETTINGS, **extra))
     r = s.solve()
-    t1 = time.perf_counter()
-    it, st = r.info.iter, r.info.solve_time
-    status = r.info.status
+    dt = time.perf_counter() - t0
     s.cleanup()
-    return it, t1 - t0, st, status
+    return r, dt
 
 
 def run_reference(args):
     rank, world, _ = dist_env()
     if rank != 0:
         return
+    mode, wl = arm_workload(args)
     lib = oracle_library()
-    pb = make_problem(CPU_SAMPLE_SCALE, seed=1)
+    pb, sample = cpu_sample_problem(wl)
     n, m = pb["P"].shape[0], pb["A"].shape[0]
     for _ in range(args.warmup):
         cpu_step(lib, pb)
     t0 = time.perf_counter()
-    iters = 0
-    solve_s = 0.0
+    iters, solve_s, status = 0, 0.0, ""
     for _ in range(args.steps):
-        it, dt, st, status = cpu_step(lib, pb)
-        iters += it
-        solve_s += st
+        r, dt = cpu_step(lib, pb)
+        iters += r.info.iter
+        solve_s += r.info.solve_time
+        status = r.info.status
     total = time.perf_counter() - t0
     v = iters / total
-    sample = (f"Lasso generator at scale {CPU_SAMPLE_SCALE}: n={n}, m={m}, nnz(A)={pb['A'].nnz}; "
-              "the full-size KKT factor does not fit QDLDL (fill ~ n_features^2)")
     out = {
         "impl": "reference", "metric": "admm_iters_per_sec", "value": v, "unit": "iter/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True, "scaling": "weak",
+        "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True,
+        "scaling": "strong" if mode == "sharded" else "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "lasso_1e5x1e6 (BASELINE configs[1]), bounded CPU sample",
-                   "sample_scale": CPU_SAMPLE_SCALE, "n": n, "m": m, "nnzA": int(pb["A"].nnz),
-                   "eps": 1e-3, "solver": "builtin + QDLDL (direct)", "step": "osqp_setup + osqp_solve"},
+        "config": {"workload": workload_name(mode, wl, args.scale) + ", bounded CPU sample", "sample": sample,
+                   "n": n, "m": m, "nnzA": int(pb["A"].nnz), "eps": 1e-3,
+                   "solver": "builtin + QDLDL (direct), 1 host thread (the builtin path is single-threaded: qdldl_interface.c:269-270)",
+                   "step": "osqp_setup + osqp_solve"},
         "cpu_baseline": {"value": v, "unit": "iter/s", "cores": 1, "kind": "reference", "sample": sample,
                          "solve_only_iters_per_sec": iters / solve_s if solve_s else None},
         "e2e": {"value": v, "unit": "iter/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -178,11 +228,23 @@ def run_reference(args):
     args.emit(json.dumps(out))
 
 
+def workload_name(mode, wl, scale):
+    if mode == "sharded":
+        base = {"svm": "svm_1e7x1e4, 1.2e8 nnz (BASELINE configs[3])", "huber": "huber_1e7x1e4, 1.5e8 nnz (BASELINE configs[3])"}[wl]
+        return base if scale == 1.0 else f"{wl} block generator at scale {scale}"
+    if wl == "lasso" and scale == 1.0:
+        return "lasso_1e5x1e6 (BASELINE configs[1])"
+    return f"{wl} generator at scale {scale}"
+
+
 # ------------------------------------------------------------------------------- B200 arm
+def spmv_bytes(r, c, nnz):
+    return nnz * (F + 4) + (r + 1) * 4 + c * F + r * F
+
+
 def pcg_roofline(k, pb, kcg):
-    """Time the dominant kernel (the persistent PCG kernel, one launch = one linear solve with
-    exactly `kcg` CG iterations) with CUDA events on the library stream; algorithmic bytes per
-    launch from SURVEY.md section 8(d)."""
+    """Time the dominant kernel with CUDA events on the library stream; algorithmic bytes per launch
+    from SURVEY.md section 8(d)."""
     import ctypes as C
     import scipy.sparse as sp
     from osqp_b200.devmem import DeviceArray, csr_to_device
@@ -213,26 +275,16 @@ def pcg_roofline(k, pb, kcg):
             times.append(ms)
     li = C.c_int(0)
     k.b200_pcg_stats(pcg, None, None, C.byref(li), None, None)
-    # graph driver (the default at this size): per-kernel CUDA-event times of one CG iteration
-    k.b200_pcg_profile_last.argtypes = [C.c_int, C.POINTER(C.c_double), C.c_int]
-    k.b200_pcg_profile_last.restype = C.c_int
-    ph = (C.c_double * 14)()
-    phases = None
-    if k.b200_pcg_profile_last(20, ph, 14) == 0:
-        phases = {"pass_A_us": ph[0], "pass_K2_us": ph[1], "update_us": ph[2], "iteration_us": ph[3],
-                  "initial_residual_pass_us": ph[5]}
+    phases = pcg_phases(k)
     k.b200_pcg_destroy(pcg)
     for h in (hP, hA, hAt):
         k.b200_csr_destroy(h)
     nnzA, nnzK = A.nnz, Pfull.nnz + A.nnz
-
-    def spmv(r, c, nnz):
-        return nnz * (F + 4) + (r + 1) * 4 + c * F + r * F
     # algorithmic bytes of what the kernel must stream (osqp_b200/csrc/pcg.cu header):
     # per CG iteration SpMV(A) + SpMV([P+sigma I | A']) + 8nF; per launch one more pass over the
     # fused operator (initial residual) + (3n+3m)F of right-hand side / write-back vectors
-    per_iter = spmv(m, n, nnzA) + spmv(n, n + m, nnzK) + 8 * n * F
-    fixed = spmv(n, n + m, nnzK) + (3 * n + 3 * m) * F
+    per_iter = spmv_bytes(m, n, nnzA) + spmv_bytes(n, n + m, nnzK) + 8 * n * F
+    fixed = spmv_bytes(n, n + m, nnzK) + (3 * n + 3 * m) * F
     byts = fixed + li.value * per_iter
     ms = float(np.mean(times))
     out = {"kernel": "pcg_kernel", "cg_iters_per_launch": li.value, "bytes_per_launch": byts,
@@ -241,18 +293,185 @@ def pcg_roofline(k, pb, kcg):
         # the dominant kernel of the graph driver is the fused-operator pass (one launch per CG
         # iteration + one per solve): its own algorithmic bytes = SpMV([P+sigma I | A']) + the
         # p, r, M^-1 reads of the three fused dot products
-        kb = spmv(n, n + m, nnzK) + 3 * n * F
+        kb = spmv_bytes(n, n + m, nnzK) + 3 * n * F
         out.update({"kernel": "g_lean_pass<1> (fused-operator pass Kp = [P+sigma I | A'][p; t] + 3 dots)",
                     "bytes_per_launch": kb, "ms_per_launch": phases["pass_K2_us"] / 1e3,
                     "gbs": kb / phases["pass_K2_us"] / 1e3,
                     "solve": {"cg_iters": li.value, "bytes": byts, "ms": ms, "gbs": byts / ms / 1e6},
-                    "pass_A": {"bytes": spmv(m, n, nnzA), "us": phases["pass_A_us"],
-                               "gbs": spmv(m, n, nnzA) / phases["pass_A_us"] / 1e3},
+                    "pass_A": {"bytes": spmv_bytes(m, n, nnzA), "us": phases["pass_A_us"],
+                               "gbs": spmv_bytes(m, n, nnzA) / phases["pass_A_us"] / 1e3},
+                    "cg_iteration": {"bytes": per_iter, "us": phases["iteration_us"],
+                                     "gbs": per_iter / phases["iteration_us"] / 1e3},
                     "phases_us": phases})
     return out
 
 
-def run_b200(args):
+def pcg_phases(k):
+    """per-kernel CUDA-event times of one CG iteration of the most recently created solver"""
+    import ctypes as C
+    k.b200_pcg_profile_last.argtypes = [C.c_int, C.POINTER(C.c_double), C.c_int]
+    k.b200_pcg_profile_last.restype = C.c_int
+    ph = (C.c_double * 14)()
+    if k.b200_pcg_profile_last(20, ph, 14) != 0:
+        return None
+    return {"pass_A_us": ph[0], "pass_K2_us": ph[1], "update_us": ph[2], "iteration_us": ph[3],
+            "initial_residual_pass_us": ph[5]}
+
+
+REFCUDA_WORKER = r'''
+import sys, time, json
+sys.path.insert(0, %(root)r)
+import numpy as np
+import bench
+from osqp_b200.interface import OSQP, LoadedLibrary
+L = LoadedLibrary(%(root)r + "/oracle/_ref/libosqp_refcuda_f64.so", np.float64)
+pb = bench.make_problem(float(sys.argv[1]), seed=1, workload=sys.argv[2])
+kw = dict(bench.SETTINGS, linsys_solver=2)
+res = []
+for rep in range(3):
+    t0 = time.perf_counter(); s = OSQP(L).setup(pb["P"], pb["q"], pb["A"], pb["l"], pb["u"], **kw); t1 = time.perf_counter()
+    r = s.solve(); t2 = time.perf_counter()
+    res.append(dict(setup_ms=1e3 * (t1 - t0), solve_ms=1e3 * (t2 - t1), iters=int(r.info.iter), status=r.info.status, obj=float(r.info.obj_val)))
+    s.cleanup()
+best = min(res[1:], key=lambda d: d["solve_ms"] + d["setup_ms"])
+print("RESULT " + json.dumps(best))
+'''
+
+
+def refcuda_block(args, wl, b200_solve_ms, b200_e2e_ms, b200_iters):
+    """The reference's OWN algebra/cuda backend (unmodified sources compiled for sm_100 by
+    oracle/Makefile `refcuda`) on the same GPU, same problem, same settings -- in a child process (it
+    exports the same symbols as the product library).  cuda_pcg_interface.cu:229-273."""
+    lib = ROOT / "oracle" / "_ref" / "libosqp_refcuda_f64.so"
+    if not lib.exists():
+        return {"unavailable": f"{lib.name} not built (make -C oracle refcuda needs /root/reference)"}
+    try:
+        p = subprocess.run([sys.executable, "-c", REFCUDA_WORKER % dict(root=str(ROOT)), str(args.scale), wl],
+                           capture_output=True, text=True, timeout=600)
+        line = [x for x in p.stdout.splitlines() if x.startswith("RESULT")]
+        if not line:
+            return {"unavailable": "worker failed: " + p.stderr[-300:]}
+        d = json.loads(line[0][7:])
+    except Exception as exc:   # noqa: BLE001 -- the block is optional
+        return {"unavailable": str(exc)}
+    d.update({"impl": "reference algebra/cuda (cuSPARSE/cuBLAS PCG), f64, same B200, same problem and settings",
+              "iters_per_sec": d["iters"] / (d["solve_ms"] / 1e3),
+              "e2e_iters_per_sec": d["iters"] / ((d["solve_ms"] + d["setup_ms"]) / 1e3),
+              "time_to_solution_ms": d["solve_ms"], "e2e_time_to_solution_ms": d["solve_ms"] + d["setup_ms"],
+              "b200_speedup_solve": d["solve_ms"] / b200_solve_ms,
+              "b200_speedup_e2e": (d["solve_ms"] + d["setup_ms"]) / b200_e2e_ms,
+              "same_iterations": d["iters"] == b200_iters})
+    return d
+
+
+ORACLE_FULL_WORKER = r'''
+import sys, time, json
+sys.path.insert(0, %(root)r)
+import bench
+lib = bench.oracle_library()
+pb = bench.make_problem(1.0, seed=1, workload="random_qp")
+r, dt = bench.cpu_step(lib, pb)
+json.dump(dict(seconds=dt, iters=int(r.info.iter), status=r.info.status, obj=float(r.info.obj_val),
+               setup_s=float(r.info.setup_time), solve_s=float(r.info.solve_time)), open(sys.argv[1], "w"))
+'''
+
+
+class OracleFullSize:
+    """BASELINE configs[0] (random QP n=1e4, m=2e4: 'builtin QDLDL on CPU') at FULL size on the oracle,
+    started in a child process on one host core while the GPU work of the bench runs; the factor of this
+    KKT system is nearly dense, a solve takes minutes, so the wait at the end is bounded."""
+
+    def __init__(self):
+        self.out = tempfile.NamedTemporaryFile("w+", suffix=".json", delete=False).name
+        self.t0 = time.perf_counter()
+        self.p = subprocess.Popen([sys.executable, "-c", ORACLE_FULL_WORKER % dict(root=str(ROOT)), self.out],
+                                  stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+
+    def result(self, wait_s):
+        try:
+            self.p.wait(timeout=max(wait_s, 0.0))
+        except subprocess.TimeoutExpired:
+            self.p.kill()
+            self.p.wait()
+            return {"finished": False, "waited_s": round(time.perf_counter() - self.t0, 1),
+                    "note": "stopped at the bench's time bound; offline on the build box: 209 s per osqp_setup + osqp_solve "
+                            "(tests/golden/baseline_random_qp_full.npz)"}
+        try:
+            d = json.loads(Path(self.out).read_text())
+            os.unlink(self.out)
+        except (OSError, ValueError) as exc:
+            return {"finished": False, "note": f"worker failed: {exc}"}
+        d["finished"] = True
+        return d
+
+
+def same_config_block(k, oracle_full, wait_s):
+    """configs[0] on both backends, end to end from host arrays: (a) a reduced instance (scale 0.3) that the
+    oracle finishes in seconds, solved by both inside this run, (b) the full-size instance on the B200
+    with the oracle's full-size time beside it when its child process finished in time."""
+    from osqp_b200 import OSQP
+    out = {"cores": 1}
+    lib = oracle_library()
+
+    def b200_e2e(pb, reps=5):
+        best = None
+        for _ in range(reps):
+            t0 = time.perf_counter()
+            s = OSQP("f64").setup(pb["P"], pb["q"], pb["A"], pb["l"], pb["u"], **SETTINGS)
+            r = s.solve()
+            dt = time.perf_counter() - t0
+            s.cleanup()
+            best = dt if best is None else min(best, dt)
+        return r, best
+    pb = make_problem(0.3, seed=1, workload="random_qp")
+    rc, dtc = cpu_step(lib, pb)
+    rg, dtg = b200_e2e(pb)
+    out["reduced"] = {"workload": f"random_qp generator at scale 0.3: n={pb['P'].shape[0]}, m={pb['A'].shape[0]}, nnz(A)={pb['A'].nnz}",
+                      "cpu": {"seconds": dtc, "iters": int(rc.info.iter), "status": rc.info.status, "obj": rc.info.obj_val,
+                              "iters_per_sec": rc.info.iter / dtc},
+                      "b200": {"seconds": dtg, "iters": int(rg.info.iter), "status": rg.info.status, "obj": rg.info.obj_val,
+                               "iters_per_sec": rg.info.iter / dtg},
+                      "e2e_time_ratio_cpu_over_b200": dtc / dtg,
+                      "obj_rel_diff": abs(rg.info.obj_val - rc.info.obj_val) / max(1.0, abs(rc.info.obj_val))}
+    pbf = make_problem(1.0, seed=1, workload="random_qp")
+    rg, dtg = b200_e2e(pbf)
+    full = {"workload": f"BASELINE configs[0]: random QP n={pbf['P'].shape[0]}, m={pbf['A'].shape[0]}, nnz(A)={pbf['A'].nnz}",
+            "b200": {"seconds": dtg, "iters": int(rg.info.iter), "status": rg.info.status, "obj": rg.info.obj_val,
+                     "iters_per_sec": rg.info.iter / dtg}}
+    if oracle_full is not None:
+        full["cpu"] = oracle_full.result(wait_s)
+        if full["cpu"].get("finished"):
+            full["e2e_time_ratio_cpu_over_b200"] = full["cpu"]["seconds"] / dtg
+            full["obj_rel_diff"] = abs(rg.info.obj_val - full["cpu"]["obj"]) / max(1.0, abs(full["cpu"]["obj"]))
+    out["full_size"] = full
+    return out
+
+
+def cpu_baseline_block(k, wl):
+    """the oracle on a bounded sample of the workload, and the B200 answer on the same sample checked
+    against it (status, objective to 5e-3 relative at eps 1e-3, primal feasibility)"""
+    from osqp_b200 import OSQP
+    lib = oracle_library()
+    cpb, sample = cpu_sample_problem(wl)
+    r, dt = cpu_step(lib, cpb)
+    cpu = {"value": r.info.iter / dt, "unit": "iter/s", "cores": 1, "kind": "reference",
+           "sample": "one osqp_setup + osqp_solve on 1 host core (unmodified reference core + builtin backend + QDLDL "
+                     "restatement): " + sample,
+           "solve_only_iters_per_sec": r.info.iter / r.info.solve_time if r.info.solve_time else None, "seconds": dt}
+    s = OSQP("f64").setup(cpb["P"], cpb["q"], cpb["A"], cpb["l"], cpb["u"], **SETTINGS)
+    rg = s.solve()
+    s.cleanup()
+    Ax = cpb["A"] @ rg.x
+    viol = float(np.maximum(np.maximum(cpb["l"] - Ax, Ax - cpb["u"]), 0).max())
+    rel = abs(rg.info.obj_val - r.info.obj_val) / max(1.0, abs(r.info.obj_val))
+    ok = (rg.info.status_val == r.info.status_val and rel <= 5e-3 and viol <= 2e-3 * (1 + max(float(np.abs(Ax).max()), 1.0)))
+    parity = {"ok": bool(ok), "status": [rg.info.status, r.info.status], "obj_rel_diff": rel, "max_violation": viol,
+              "iters": [int(rg.info.iter), int(r.info.iter)], "on": "the CPU sample above, B200 backend vs oracle"}
+    return cpu, parity
+
+
+def run_single(args):
+    """one GPU per rank, every rank its own QP (N = 1: the headline configuration)"""
     rank, world, local = dist_env()
     dist = None
     if world > 1:
@@ -260,27 +479,19 @@ def run_b200(args):
         import torch.distributed as dist
         torch.cuda.set_device(local)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    from osqp_b200 import OSQP, problems
+    from osqp_b200 import OSQP
     from osqp_b200.devmem import kernels
     prec = args.dtype
-    sharded = args.mode == "sharded" and world > 1
-    if sharded:
-        # ONE QP, rows of A split over the ranks, one all-reduce of the length-n partial per K.p
-        from osqp_b200.dist import ShardedOSQP, init_sharded
-        k = init_sharded(dist, local, prec)
-        kernels(prec)
-        pb = make_problem(args.scale, seed=1, workload=args.workload)
-        _Base = OSQP
-
-        def OSQP(_prec):  # noqa: N802 -- same constructor signature as the single-GPU class
-            return ShardedOSQP(rank, world, _prec)
-    else:
-        k = kernels(prec)
-        if k.b200_init(local) != 0:
-            raise RuntimeError("no usable GPU: the B200 backend has no CPU fallback")
-        # same generator and seed on every rank: per-GPU work is identical, which is what "weak"
-        # scaling compares (each rank still builds, uploads and solves its own copy)
-        pb = make_problem(args.scale, seed=1, workload=args.workload)
+    mode, wl = arm_workload(args)
+    k = kernels(prec)
+    if k.b200_init(local) != 0:
+        raise RuntimeError("no usable GPU: the B200 backend has no CPU fallback")
+    extras = world == 1 and prec == "f64" and not args.no_cpu_baseline
+    oracle_full = OracleFullSize() if (extras and not args.no_same_config) else None
+    t_start = time.perf_counter()
+    # same generator and seed on every rank: per-GPU work is identical, which is what "weak"
+    # scaling compares (each rank still builds, uploads and solves its own copy)
+    pb = make_problem(args.scale, seed=1, workload=wl)
     n, m = pb["P"].shape[0], pb["A"].shape[0]
     nnzA, nnzP = int(pb["A"].nnz), int(pb["P"].nnz)
 
@@ -315,7 +526,6 @@ def run_b200(args):
     cg1, ns1 = solver.cg_stats()
     # a graph launch is one enqueue but 1 + 3 k kernels (loop-init node, then A pass / operator
     # pass / fused update per CG iteration): count the kernels, not the enqueues
-    k.b200_graph_launch_count.restype = ctypes.c_ulonglong
     if k.b200_graph_launch_count() - g0 > 0:
         launches += 3 * (cg1 - cg0)
     status, obj = r.info.status, r.info.obj_val
@@ -343,9 +553,9 @@ def run_b200(args):
     barrier()
     e_total = time.perf_counter() - t0
     fi = F if prec == "f64" else 4
-    # uploads of one setup: CSC(A) once (= CSR(A'); CSR(A) is built on the device), the full symmetric
-    # P expanded on the host, q / l / u
-    h2d = nnzA * (fi + 4) + (n + 1) * 4 + (2 * nnzP + n) * (fi + 4) + (n + 1) * 4 + (n + 2 * m) * fi
+    # uploads of one setup: CSC(A) once (= CSR(A'); CSR(A) is built on the device), the upper triangle of P
+    # (expanded on the device), q / l / u
+    h2d = nnzA * (fi + 4) + (n + 1) * 4 + nnzP * (fi + 4) + (n + 1) * 4 + (n + 2 * m) * fi
     d2h = 2 * (n + m) * fi
 
     # ---- aggregate over ranks: max time, summed work
@@ -357,15 +567,13 @@ def run_b200(args):
         dist.all_reduce(w, op=dist.ReduceOp.SUM)
         ms, e_total = t.tolist()
         iters, e_iters, launches, dcg, dns = w.tolist()
-        if sharded:     # every rank ran the SAME iterations of the one shared QP
-            iters, e_iters, dcg, dns = iters / world, e_iters / world, dcg / world, dns / world
     else:
         dcg, dns = cg1 - cg0, ns1 - ns0
 
     if rank == 0:
         peak, peak_src = peaks()
         kcg = max(1, int(round(dcg / max(dns, 1))))
-        roof = pcg_roofline(k, pb, kcg) if (prec == "f64" and not sharded) else None
+        roof = pcg_roofline(k, pb, kcg) if prec == "f64" else None
         traffic = None
         tp = ROOT / "profiles" / "pcg_traffic.json"
         if tp.exists() and roof is not None:
@@ -378,38 +586,20 @@ def run_b200(args):
                     traffic = tj.get("dram_bytes_per_launch")
             except (ValueError, OSError):
                 traffic = None
-        cpu = None
-        if world == 1 and not args.no_cpu_baseline:
-            try:
-                lib = oracle_library()
-                cpb = make_problem(CPU_SAMPLE_SCALE, seed=1)
-                it, dt, st, _ = cpu_step(lib, cpb)
-                cpu = {"value": it / dt, "unit": "iter/s", "cores": 1, "kind": "reference",
-                       "sample": (f"one osqp_setup + osqp_solve of the Lasso generator at scale "
-                                  f"{CPU_SAMPLE_SCALE} (n={cpb['P'].shape[0]}, m={cpb['A'].shape[0]}, "
-                                  f"nnz(A)={cpb['A'].nnz}) on 1 host core: unmodified reference core + "
-                                  "builtin backend + QDLDL restatement; full size does not fit QDLDL"),
-                       "solve_only_iters_per_sec": it / st if st else None, "seconds": dt}
-            except Exception as exc:   # the oracle is optional for the product arm
-                cpu = {"value": None, "unit": "iter/s", "cores": 1, "kind": "reference",
-                       "sample": f"unavailable: {exc}"}
         out = {
             "metric": "admm_iters_per_sec", "value": iters / (ms / 1e3), "unit": "iter/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms / args.steps, "higher_is_better": True,
-            "scaling": "strong" if sharded else "weak",
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": prec, "data": "synthetic",
-            "config": {"workload": ("lasso_1e5x1e6 (BASELINE configs[1])" if (args.scale == 1.0 and args.workload == "lasso")
-                                    else f"{args.workload} generator at scale {args.scale}"),
+            "config": {"workload": workload_name(mode, wl, args.scale),
                        "n": n, "m": m, "nnzA": nnzA, "nnzP": nnzP, "eps": 1e-3,
                        "solver": "indirect: device-resident Jacobi PCG on the reduced KKT system (CUDA-graph WHILE loop of lean sm_100a passes)",
                        "step": "one cold-start osqp_solve to eps 1e-3",
                        "parallelism": ("1 GPU" if world == 1 else
-                                       (f"one QP row-sharded over {world} GPUs, column-split layout: 1 NCCL all-reduce of the shared columns + 2 scalar exchanges per CG iteration"
-                                        if sharded else f"{world} independent QPs (same generator and seed), one per GPU, no comms")),
+                                       f"{world} independent QPs (same generator and seed), one per GPU, no comms"),
                        "l2_policy": "working set (>=460 MB of matrices per CG iteration) exceeds the 126 MB L2",
                        "settings": {kk: vv for kk, vv in SETTINGS.items()}},
-            "admm_iters_per_step": iters / args.steps / (1 if sharded else world),
+            "admm_iters_per_step": iters / args.steps / world,
             "cg_iters_per_admm_iter": dcg / max(dns, 1),
             "time_to_solution_ms": ms / args.steps,
             "status": status, "obj_val": obj,
@@ -426,15 +616,242 @@ def run_b200(args):
                                "kernel": roof["kernel"], "cg_iters_per_launch": roof["cg_iters_per_launch"],
                                "bytes_per_launch": roof["bytes_per_launch"],
                                "ms_per_launch": roof["ms_per_launch"]}
-            for extra in ("solve", "pass_A", "phases_us"):
+            for extra in ("solve", "pass_A", "cg_iteration", "phases_us"):
                 if extra in roof:
                     out["roofline"][extra] = roof[extra]
+                    if isinstance(roof[extra], dict) and "gbs" in roof[extra]:
+                        out["roofline"][extra]["frac"] = roof[extra]["gbs"] / peak
+        cpu = None
+        if extras:
+            try:
+                cpu, out["parity"] = cpu_baseline_block(k, wl)
+            except Exception as exc:   # noqa: BLE001 -- the oracle is optional for the product arm
+                cpu = {"value": None, "unit": "iter/s", "cores": 1, "kind": "reference", "sample": f"unavailable: {exc}"}
+            if not args.no_ref_cuda:
+                out["ref_cuda"] = refcuda_block(args, wl, ms / args.steps, 1e3 * e_total / args.steps,
+                                                iters / args.steps)
+            if not args.no_same_config:
+                try:
+                    # the full-size oracle solve gets what is left of a 5-minute bench
+                    out["cpu_baseline_same_config"] = same_config_block(
+                        k, oracle_full, args.same_config_budget - (time.perf_counter() - t_start))
+                except Exception as exc:   # noqa: BLE001
+                    out["cpu_baseline_same_config"] = {"unavailable": str(exc)}
         out["cpu_baseline"] = cpu
         args.emit(json.dumps(out))
     if dist is not None:
         dist.barrier()
-        if sharded:
-            k.b200_dist_finalize()
+        dist.destroy_process_group()
+
+
+def run_sharded(args):
+    """ONE QP, rows of A split over the ranks (strong scaling).  world = 1 solves the same global QP on
+    one GPU through the ordinary single-GPU path."""
+    rank, world, local = dist_env()
+    import ctypes as C
+    from osqp_b200 import OSQP
+    from osqp_b200.devmem import kernels
+    prec = args.dtype
+    mode, wl = arm_workload(args)
+    dist = None
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        from osqp_b200.dist import ShardedOSQP, init_sharded
+        k = init_sharded(dist, local, prec)
+        kernels(prec)
+    else:
+        k = kernels(prec)
+        if k.b200_init(local) != 0:
+            raise RuntimeError("no usable GPU: the B200 backend has no CPU fallback")
+    k.b200_dist_p2p_enabled.restype = C.c_int
+    p2p = bool(k.b200_dist_p2p_enabled()) if world > 1 else False
+    t_gen = time.perf_counter()
+    sh = make_shard(rank, world, wl, args.scale)
+    t_gen = time.perf_counter() - t_gen
+    n_loc, m_loc = sh["A"].shape[1], sh["A"].shape[0]
+    nnzA_loc, nnzP_loc = int(sh["A"].nnz), int(sh["P"].nnz)
+
+    def new_solver():
+        if world > 1:
+            return ShardedOSQP(rank, world, prec).setup_local(sh, sh["n_global"], sh["m_global"], **SETTINGS)
+        return OSQP(prec).setup(sh["P"], sh["q"], sh["A"], sh["l"], sh["u"], **SETTINGS)
+
+    def barrier():
+        k.b200_sync()
+        if dist is not None:
+            import torch
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    solver = new_solver()
+    for _ in range(args.warmup):
+        r = solver.solve()
+    cg0, ns0 = solver.cg_stats()
+    e0, e1 = k.b200_event_create(), k.b200_event_create()
+    sampler = ClockSampler(local) if rank == 0 else None
+    k.b200_dist_stats.argtypes = [C.POINTER(C.c_ulonglong), C.POINTER(C.c_ulonglong)]
+    nc0, nb0 = C.c_ulonglong(0), C.c_ulonglong(0)
+    k.b200_dist_stats(C.byref(nc0), C.byref(nb0))
+    barrier()
+    l0 = k.b200_launch_count()
+    k.b200_graph_launch_count.restype = C.c_ulonglong
+    g0 = k.b200_graph_launch_count()
+    k.b200_event_record(e0)
+    iters = 0
+    for _ in range(args.steps):
+        r = solver.solve()
+        iters += r.info.iter
+    k.b200_event_record(e1)
+    ms = k.b200_event_elapsed_ms(e0, e1)
+    launches = k.b200_launch_count() - l0
+    barrier()
+    clocks = sampler.stop() if sampler else None
+    cg1, ns1 = solver.cg_stats()
+    nc1, nb1 = C.c_ulonglong(0), C.c_ulonglong(0)
+    k.b200_dist_stats(C.byref(nc1), C.byref(nb1))
+    if k.b200_graph_launch_count() - g0 > 0:
+        launches += (4 if p2p else 3) * (cg1 - cg0)
+    status, obj = r.info.status, r.info.obj_val
+    phases = pcg_phases(k) if prec == "f64" else None     # this rank's passes, timed alone (no exchange)
+    solver.cleanup()
+
+    # ---- end to end: this rank's shard from host arrays -> setup -> solve -> its slice of the solution
+    def e2e_step():
+        t0 = time.perf_counter()
+        s = new_solver()
+        t1 = time.perf_counter()
+        rr = s.solve()
+        t2 = time.perf_counter()
+        s.cleanup()
+        return rr.info.iter, t2 - t0, t1 - t0
+    e2e_steps = max(1, min(args.steps, args.sharded_e2e_steps))
+    e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    e_iters, setup_s = 0, 0.0
+    for _ in range(e2e_steps):
+        it, dt, st = e2e_step()
+        e_iters += it
+        setup_s += st
+    barrier()
+    e_total = time.perf_counter() - t0
+    fi = F if prec == "f64" else 4
+    h2d = nnzA_loc * (fi + 4) + (n_loc + 1) * 4 + nnzP_loc * (fi + 4) + (n_loc + 1) * 4 + (n_loc + 2 * m_loc) * fi
+    d2h = 2 * (n_loc + m_loc) * fi
+    dcg, dns = cg1 - cg0, ns1 - ns0
+    nnzA_all, h2d_all, d2h_all = nnzA_loc, h2d, d2h
+    if dist is not None:
+        import torch
+        t = torch.tensor([ms, e_total, t_gen], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms, e_total, t_gen = t.tolist()
+        w = torch.tensor([launches, nnzA_loc, h2d, d2h], device="cuda", dtype=torch.float64)
+        dist.all_reduce(w, op=dist.ReduceOp.SUM)
+        launches, nnzA_all, h2d_all, d2h_all = w.tolist()
+
+    # ---- strong-scaling reference inside the same run: rank 0 solves the WHOLE QP on its own GPU
+    strong = None
+    if world > 1 and not args.no_strong_baseline:
+        if rank == 0:
+            k.b200_dist_suspend(1)
+            try:
+                from osqp_b200 import load_library
+                load_library(prec).lib.osqp_b200_dist_configure(0, -1)
+                tg = time.perf_counter()
+                whole = make_shard(0, 1, wl, args.scale)
+                tg = time.perf_counter() - tg
+                ts = time.perf_counter()
+                s1 = OSQP(prec).setup(whole["P"], whole["q"], whole["A"], whole["l"], whole["u"], **SETTINGS)
+                ts = time.perf_counter() - ts
+                s1.solve()
+                f0, f1 = k.b200_event_create(), k.b200_event_create()
+                k.b200_event_record(f0)
+                reps, it1 = 3, 0
+                for _ in range(reps):
+                    r1 = s1.solve()
+                    it1 += r1.info.iter
+                k.b200_event_record(f1)
+                ms1 = k.b200_event_elapsed_ms(f0, f1) / reps
+                cgw, nsw = s1.cg_stats()
+                s1.cleanup()
+                strong = {"single_gpu_ms_per_solve": ms1, "single_gpu_iters": it1 / reps, "single_gpu_status": r1.info.status,
+                          "single_gpu_obj": r1.info.obj_val, "single_gpu_setup_ms": 1e3 * ts,
+                          "single_gpu_cg_per_admm": cgw / max(nsw, 1),
+                          "n_gpu_ms_per_solve": ms / args.steps, "speedup": ms1 / (ms / args.steps),
+                          "efficiency": ms1 / (ms / args.steps) / world,
+                          "same_iterations": it1 / reps == iters / args.steps,
+                          "obj_rel_diff": abs(r1.info.obj_val - obj) / max(1.0, abs(obj)),
+                          "note": "same global QP (block-seeded generator), solved by rank 0 alone on its GPU in this run; "
+                                  f"generation of the whole problem {tg:.0f} s on one host core is outside every timed region"}
+                del whole
+            finally:
+                k.b200_dist_suspend(0)
+        dist.barrier()
+
+    if rank == 0:
+        peak, peak_src = peaks()
+        n_glob, m_glob = sh["n_global"], sh["m_global"]
+        out = {
+            "metric": "admm_iters_per_sec", "value": iters / (ms / 1e3), "unit": "iter/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": prec, "data": "synthetic",
+            "config": {"workload": workload_name(mode, wl, args.scale),
+                       "n": n_glob, "m": m_glob, "nnzA": int(nnzA_all), "eps": 1e-3,
+                       "rank0_shard": {"n_local": n_loc, "m_local": m_loc, "nnzA_local": nnzA_loc, "n_shared": int(sh["n_shared"])},
+                       "solver": "indirect: device-resident Jacobi PCG on the reduced KKT system (CUDA-graph WHILE loop of lean sm_100a passes)",
+                       "step": "one cold-start osqp_solve of the ONE global QP to eps 1e-3",
+                       "parallelism": ("1 GPU (whole QP)" if world == 1 else
+                                       f"one QP, rows of A split over {world} GPUs, column-split layout (shared feature columns, owned slack "
+                                       "columns); per CG iteration " +
+                                       ("ONE peer-memory exchange kernel (NVLink P2P stores of the n_shared-long head of K p + 3 dot partials "
+                                        "into every peer, folded in rank order) + a 2-scalar peer exchange in the tail of the fused update; "
+                                        "no NCCL call, no host synchronisation inside the CG loop (CUDA-graph WHILE node)" if p2p else
+                                        "1 NCCL all-reduce of the shared columns + 2 scalar all-reduces, host-driven loop")),
+                       "generation": f"every rank draws only its own sample blocks ({t_gen:.1f} s, outside every timed region)",
+                       "l2_policy": "per-rank working set exceeds the 126 MB L2" if nnzA_loc * 24 > 126e6 else "per-rank matrices partly L2 resident",
+                       "settings": {kk: vv for kk, vv in SETTINGS.items()}},
+            "admm_iters_per_step": iters / args.steps,
+            "cg_iters_per_admm_iter": dcg / max(dns, 1),
+            "time_to_solution_ms": ms / args.steps,
+            "status": status, "obj_val": obj,
+            "e2e": {"value": e_iters / e_total, "unit": "iter/s", "h2d_bytes_per_step": h2d_all,
+                    "d2h_bytes_per_step": d2h_all, "time_to_solution_ms": 1e3 * e_total / e2e_steps,
+                    "setup_ms": 1e3 * setup_s / e2e_steps, "steps": e2e_steps,
+                    "step": "per rank: osqp_setup of its shard from host CSC arrays + osqp_solve + its slice of the solution to host"},
+            "gpu_launches": int(launches),
+            "exchange": {"p2p": p2p,
+                         "nccl_allreduce_calls_per_solve": (nc1.value - nc0.value) / args.steps,
+                         "nccl_allreduce_calls_per_cg_iter_inside_loop": 0 if p2p else 3,
+                         "nccl_bytes_per_solve": (nb1.value - nb0.value) / args.steps,
+                         "peer_exchanges_per_cg_iter": 2 if p2p else 0,
+                         "peer_bytes_per_cg_iter_per_rank": (int(sh["n_shared"]) + 3 + 2) * 8 * (world - 1) if p2p else 0,
+                         "host_syncs_per_cg_iter": 0 if (p2p or world == 1) else 1},
+            "clocks": clocks,
+        }
+        if strong is not None:
+            out["strong_scaling"] = strong
+        if phases is not None:
+            # per-rank roofline of the two passes of one CG iteration, timed alone on rank 0's shard
+            from osqp_b200 import problems as _pr
+            nnzK = nnzA_loc + _pr.nnz_P_full(sh["P"])     # [P + sigma I | A_r'] with a structurally full diagonal
+            kb = spmv_bytes(n_loc, n_loc + m_loc, nnzK) + 3 * n_loc * F
+            ab = spmv_bytes(m_loc, n_loc, nnzA_loc)
+            out["roofline"] = {"bound": "hbm", "achieved": kb / phases["pass_K2_us"] / 1e3, "peak": peak, "unit": "GB/s",
+                               "frac": kb / phases["pass_K2_us"] / 1e3 / peak, "traffic": None, "peak_source": peak_src,
+                               "kernel": "fused-operator pass over rank 0's shard [P + sigma I | A_r'] (timed alone, no exchange)",
+                               "bytes_per_launch": kb, "ms_per_launch": phases["pass_K2_us"] / 1e3,
+                               "pass_A": {"bytes": ab, "us": phases["pass_A_us"], "gbs": ab / phases["pass_A_us"] / 1e3,
+                                          "frac": ab / phases["pass_A_us"] / 1e3 / peak},
+                               "phases_us": phases}
+        out["cpu_baseline"] = None
+        args.emit(json.dumps(out))
+    if dist is not None:
+        dist.barrier()
+        k.b200_dist_finalize()
         dist.destroy_process_group()
 
 
@@ -465,12 +882,19 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--scale", type=float, default=1.0, help="problem scale (1.0 = BASELINE configs[1])")
+    ap.add_argument("--scale", type=float, default=1.0, help="problem scale (1.0 = the BASELINE size of the workload)")
     ap.add_argument("--dtype", default="f64", choices=["f64", "f32"])
-    ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--mode", default="batch", choices=["batch", "sharded"],
-                    help="N > 1: independent QPs per GPU (default, no comms) or ONE row-sharded QP")
-    ap.add_argument("--workload", default="lasso",
+    ap.add_argument("--no-cpu-baseline", action="store_true", help="skip cpu_baseline / parity / ref_cuda / same-config blocks")
+    ap.add_argument("--no-ref-cuda", action="store_true")
+    ap.add_argument("--no-same-config", action="store_true")
+    ap.add_argument("--same-config-budget", type=float, default=280.0,
+                    help="seconds after which the full-size oracle solve of configs[0] is abandoned")
+    ap.add_argument("--no-strong-baseline", action="store_true")
+    ap.add_argument("--sharded-e2e-steps", type=int, default=5)
+    ap.add_argument("--mode", default="auto", choices=["auto", "single", "batch", "sharded"],
+                    help="auto: ONE row-sharded QP under torchrun, the single-GPU headline otherwise; "
+                         "batch: N independent QPs, one per GPU")
+    ap.add_argument("--workload", default=None,
                     choices=["lasso", "portfolio", "huber", "svm", "random_qp", "mpc"])
     args = ap.parse_args()
     if args.warmup < 1:
@@ -479,8 +903,10 @@ def main():
         args.emit = q.emit
         if args.impl == "reference":
             run_reference(args)
+        elif arm_workload(args)[0] == "sharded":
+            run_sharded(args)
         else:
-            run_b200(args)
+            run_single(args)
 
 
 if __name__ == "__main__":

@@ -268,6 +268,9 @@ int  b200_dist_init(int rank, int world, const unsigned char* id128);   /* after
 void b200_dist_finalize(void);
 int  b200_dist_world(void);
 int  b200_dist_rank(void);
+/* while suspended the process behaves as a single-GPU process (world 1): lets one rank of a sharded job
+ * solve a whole problem on its own GPU, e.g. the single-GPU leg of a strong-scaling measurement */
+void b200_dist_suspend(int on);
 /* while the scope is 1, the scalar-returning reductions combine their result across ranks (max or
  * sum as appropriate) before handing it to the host: set by the backend around reductions over
  * row-sharded vectors */
@@ -281,6 +284,13 @@ int  b200_dist_n_shared(void);
 void b200_dist_allreduce_sum(b200_float* d_buf, int n);   /* in place, library stream */
 void b200_dist_allreduce_max(b200_float* d_buf, int n);
 void b200_dist_stats(unsigned long long* n_calls, unsigned long long* bytes);
+/* Peer-memory exchange for the CG loop of the row-sharded solve (NVLink P2P stores instead of NCCL
+ * calls).  After b200_dist_init: every rank exports the 64-byte CUDA IPC handle
+ * of its exchange buffer, the host program all-gathers the handles (rank order) and every rank imports
+ * them.  Without these two calls the sharded solve keeps its NCCL path. */
+int  b200_dist_p2p_export(unsigned char* handle64);
+int  b200_dist_p2p_import(const unsigned char* handles, int world);   /* world x 64 bytes */
+int  b200_dist_p2p_enabled(void);
 
 /* bumped by every kernel launch / device copy of the library: lets the backend cache scalars and
  * know when they went stale */

@@ -111,6 +111,35 @@ bool upload(void* d_dst, const void* h_src, size_t bytes);
 // false (after synchronising the stream) if the stream finished or failed without posting it.
 bool mail_wait(unsigned long long seq);
 
+// ---- peer-memory exchange of the row-sharded CG loop (dist.cu, pcg_graph.cu)
+// Every rank owns one exchange buffer; rank q's contribution to rank r lands in slot q of r's buffer.
+// Two sets of slots alternate with the parity of the exchange's sequence number: a rank can run at
+// most one exchange ahead of its slowest peer (every exchange waits for all peers), so the set being
+// written is never the one still being read.
+constexpr int    kXchgMaxWorld     = 8;
+constexpr int    kXchgCap          = 1 << 17;                                  // doubles per vector slot
+constexpr size_t kXchgFlagOff      = (size_t)2 * kXchgMaxWorld * kXchgCap;      // 2 x 8 vector sequence words
+constexpr size_t kXchgScOff        = kXchgFlagOff + 2 * kXchgMaxWorld;          // 2 x 8 x 4 scalar payload
+constexpr size_t kXchgScFlagOff    = kXchgScOff + 2 * kXchgMaxWorld * 4;        // 2 x 8 scalar sequence words
+constexpr size_t kXchgTotalDoubles = kXchgScFlagOff + 2 * kXchgMaxWorld + 16;
+struct XchgState {            // device memory behind the buffer; identical on all ranks by construction
+  unsigned long long vseq, sseq;   // vector / scalar exchanges completed so far
+  unsigned ticket, ticket2;
+  int err, pad;                    // 1: a wait ran into its time limit (a peer never arrived)
+};
+struct XchgView {
+  double*    mine;
+  double*    peer[kXchgMaxWorld];  // peer[r]: rank r's buffer mapped into this process (peer[rank] == mine)
+  XchgState* state;
+  int        world, rank;
+};
+__host__ __device__ inline size_t xchg_vec(int set, int r) { return ((size_t)set * kXchgMaxWorld + r) * kXchgCap; }
+__host__ __device__ inline size_t xchg_vflag(int set, int r) { return kXchgFlagOff + (size_t)set * kXchgMaxWorld + r; }
+__host__ __device__ inline size_t xchg_sc(int set, int r) { return kXchgScOff + ((size_t)set * kXchgMaxWorld + r) * 4; }
+__host__ __device__ inline size_t xchg_scflag(int set, int r) { return kXchgScFlagOff + (size_t)set * kXchgMaxWorld + r; }
+bool dist_p2p_ready();
+const XchgView& dist_xchg_view();
+
 // dist.cu
 bool dist_active();
 bool dist_scope();

@@ -30,6 +30,7 @@ struct Dist {
   fn_errstr errstr = nullptr;
   nccl_comm_t comm = nullptr;
   int rank = 0, world = 1, scope = 0;
+  int suspended = 0;     // b200_dist_suspend: solvers created meanwhile are plain single-GPU solvers
   int n_shared = -1;     // >= 0: column-split layout, n-vectors are [shared (replicated) ; local (owned)]
   unsigned long long n_allreduce = 0, bytes_allreduce = 0;
 };
@@ -69,7 +70,7 @@ bool nccl_ok(int rc, const char* what) {
 namespace b200 {
 // used by the reductions in vec_kernels.cu: combine a device scalar block across ranks when the
 // backend declared the operand row-sharded
-bool dist_active() { return g.comm != nullptr && g.world > 1; }
+bool dist_active() { return g.comm != nullptr && g.world > 1 && !g.suspended; }
 bool dist_scope() { return dist_active() && g.scope; }
 // column-split layout: every n-vector is [shared columns (replicated on all ranks) ; local columns
 // (owned by this rank)].  A reduction over such a vector counts the shared slice on rank 0 only.
@@ -85,6 +86,41 @@ void dist_allreduce_f64(double* d_buf, int n, bool is_max) {
   g.bytes_allreduce += (unsigned long long)n * 8;
 }
 }  // namespace b200
+
+// ------------------------------------------------------------------ peer-memory exchange (NVLink P2P)
+// The CG loop of the row-sharded solve exchanges (a) the n_shared-long head of the partial K p plus three
+// dot-product partials and (b) two scalars per iteration.  Through NCCL that is 3 collectives of 14-19 us
+// each plus a host read-back (profiles/r01_sharded_scaling.md); here every rank PUSHES its contribution
+// straight into a slot of every peer's exchange buffer (plain stores to cudaIpc-mapped peer memory,
+// __threadfence_system, release-store of a sequence number) from inside the producing kernels, and folds
+// what it received in rank order -- bit-identical on all ranks, no host involvement, so the loop can be a
+// CUDA-graph WHILE node exactly as on one GPU (pcg_graph.cu).  The buffer is cudaMalloc'ed (IPC handles
+// cannot be taken from the stream-ordered pool) and the 64-byte handles travel through the host program.
+namespace {
+struct P2P {
+  double* mine = nullptr;
+  double* peer[kXchgMaxWorld] = {nullptr};
+  XchgState* state = nullptr;
+  int ready = 0;
+};
+P2P p2p;
+}  // namespace
+
+namespace b200 {
+XchgView g_xchg_view;
+bool dist_p2p_ready() { return p2p.ready && dist_active() && g.world <= kXchgMaxWorld; }
+const XchgView& dist_xchg_view() { return g_xchg_view; }
+}  // namespace b200
+
+static void p2p_release() {
+  if (!p2p.mine) return;
+  cudaDeviceSynchronize();
+  for (int r = 0; r < kXchgMaxWorld; r++)
+    if (p2p.peer[r] && p2p.peer[r] != p2p.mine) cudaIpcCloseMemHandle(p2p.peer[r]);
+  cudaFree(p2p.mine);
+  p2p = P2P();
+}
+static void p2p_release_hook() { p2p_release(); }
 
 extern "C" {
 
@@ -109,6 +145,7 @@ int b200_dist_init(int rank, int world, const unsigned char* id128) {
 }
 
 void b200_dist_finalize(void) {
+  p2p_release_hook();
   if (g.comm) {
     cudaStreamSynchronize(ctx().stream);
     g.destroy(g.comm);
@@ -118,8 +155,9 @@ void b200_dist_finalize(void) {
   g.rank = 0;
 }
 
-int b200_dist_world(void) { return g.world; }
-int b200_dist_rank(void) { return g.rank; }
+int b200_dist_world(void) { return g.suspended ? 1 : g.world; }
+int b200_dist_rank(void) { return g.suspended ? 0 : g.rank; }
+void b200_dist_suspend(int on) { g.suspended = on ? 1 : 0; }
 void b200_dist_scope(int sharded) { g.scope = sharded; }
 void b200_dist_set_split(int n_shared) { g.n_shared = n_shared; }
 int  b200_dist_n_shared(void) { return g.n_shared; }
@@ -143,6 +181,45 @@ void b200_dist_allreduce_max(T* d_buf, int n) {
   g.n_allreduce++;
   g.bytes_allreduce += (unsigned long long)n * sizeof(T);
 }
+
+int b200_dist_p2p_export(unsigned char* handle64) {
+  if (!p2p.mine) {
+    const size_t bytes = sizeof(double) * kXchgTotalDoubles + sizeof(XchgState);
+    if (!B200_CHECK(cudaMalloc((void**)&p2p.mine, bytes))) return 1;
+    if (!B200_CHECK(cudaMemset(p2p.mine, 0, bytes))) return 1;
+    if (!B200_CHECK(cudaDeviceSynchronize())) return 1;
+  }
+  cudaIpcMemHandle_t h;
+  if (!B200_CHECK(cudaIpcGetMemHandle(&h, p2p.mine))) return 1;
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+  memcpy(handle64, &h, 64);
+  return 0;
+}
+
+int b200_dist_p2p_import(const unsigned char* handles, int world) {
+  if (world != g.world || world > kXchgMaxWorld || !p2p.mine) return 1;
+  for (int r = 0; r < world; r++) {
+    if (r == g.rank) { p2p.peer[r] = p2p.mine; continue; }
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handles + 64 * (size_t)r, 64);
+    void* ptr = nullptr;
+    if (!B200_CHECK(cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess))) return 1;
+    p2p.peer[r] = (double*)ptr;
+  }
+  XchgView v;
+  memset(&v, 0, sizeof(v));
+  v.mine = p2p.mine;
+  for (int r = 0; r < world; r++) v.peer[r] = p2p.peer[r];
+  v.state = (XchgState*)(p2p.mine + kXchgTotalDoubles);
+  v.world = world;
+  v.rank = g.rank;
+  g_xchg_view = v;
+  p2p.ready = 1;
+  return 0;
+}
+
+int b200_dist_p2p_enabled(void) { return dist_p2p_ready() ? 1 : 0; }
+
 
 void b200_dist_stats(unsigned long long* n_calls, unsigned long long* bytes) {
   if (n_calls) *n_calls = g.n_allreduce;

@@ -412,6 +412,7 @@ int b200_pcg_solve(b200_pcg* s, T* d_b, int admm_iter, double prim_res, double d
   a.K2 = s->K2.view();
   if (s->m > 0) { a.A = s->A->view(); a.At = s->At->view(); }   // m == 0: no A phases at all
   a.n = s->n; a.m = s->m;
+  a.n_shared = (s->sharded && dist_split()) ? dist_n_shared() : 0;
   a.x = s->d_x; a.p = s->d_p; a.Kp = s->d_Kp; a.r = s->d_r; a.t = s->d_t; a.b = d_b;
   a.Ax = s->d_Ax; a.w = s->d_w;
   // carried A x: recomputed exactly when stale, when polishing, and every kAxResync solves

@@ -35,6 +35,7 @@ struct PcgState {
 struct PcgArgs {
   CsrView K2, A, At;
   int n, m;
+  int n_shared;   // row-sharded, column-split layout: leading columns shared by several ranks (else 0)
   T *x, *p, *Kp, *r, *t, *b, *Ax, *w;
   const T* minv;
   const T* rho_vec;
@@ -78,6 +79,7 @@ struct b200_pcg {
   int use_graph = 0;
   int sharded = 0;       // row-sharded multi-GPU mode (dist.cu)
   int lean = 0;          // loop body uses the flat 32-register passes
+  int p2p = 0;           // row-sharded: exchanges go through peer memory inside the kernels, loop is a graph
   int include_P = 1;     // sharded: only rank 0 carries P + sigma I in the fused operator
   b200::PcgArgs* d_args = nullptr;
   b200::PcgRun*  d_run  = nullptr;

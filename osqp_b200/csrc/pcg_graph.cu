@@ -119,6 +119,63 @@ __device__ __forceinline__ bool publish_fold(const double* part, const int* slot
 // one extra L1 wavefront per use in the per-row epilogues: 17 us of a 70 us pass.)
 __constant__ PcgArgs c_args[kMaxContexts];   // one block per library context (host thread)
 
+// ---- peer-memory exchange (row-sharded solve; buffers and protocol: common.cuh / dist.cu) -------------
+__constant__ XchgView c_xchg;
+constexpr unsigned long long kXchgTimeoutNs = 20ull * 1000ull * 1000ull * 1000ull;   // a peer that never arrives
+
+__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
+  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+// spin until the sequence word reaches `seq` (written by a peer over NVLink); bounded, so that a rank
+// whose peer died reports an error instead of hanging the GPU
+__device__ __forceinline__ bool xchg_wait(const unsigned long long* flag, unsigned long long seq) {
+  const unsigned long long t0 = globaltimer_ns();
+  unsigned spins = 0;
+  while (ld_acquire_sys(flag) < seq) {
+    if ((++spins & 1023u) == 0 && globaltimer_ns() - t0 > kXchgTimeoutNs) return false;
+  }
+  return true;
+}
+// ALL threads of ONE CTA: this rank's (a, b) goes to every peer, the peers' pairs come back; returns
+// the sum of the a's and the maximum of the b's, folded in rank order (bit-identical on all ranks)
+__device__ __forceinline__ void xchg_scalars(double a_loc, double b_loc, double& a_sum, double& b_max) {
+  const XchgView& X = c_xchg;
+  XchgState* S = X.state;
+  const int me = X.rank, world = X.world, tid = threadIdx.x;
+  const unsigned long long seq = *(volatile unsigned long long*)&S->sseq + 1;
+  const int set = (int)(seq & 1ull);
+  if (tid < world && tid != me) {
+    double* dst = X.peer[tid] + xchg_sc(set, me);
+    dst[0] = a_loc;
+    dst[1] = b_loc;
+    __threadfence_system();
+    st_release_sys((unsigned long long*)(X.peer[tid] + xchg_scflag(set, me)), seq);
+    if (!xchg_wait((const unsigned long long*)(X.mine + xchg_scflag(set, tid)), seq)) S->err = 1;
+  }
+  __syncthreads();
+  double s = 0.0, mx = 0.0;
+  for (int r = 0; r < world; r++) {
+    const double av = (r == me) ? a_loc : __ldcg(X.mine + xchg_sc(set, r));
+    const double bv = (r == me) ? b_loc : __ldcg(X.mine + xchg_sc(set, r) + 1);
+    s += av;
+    mx = fmax(mx, bv);
+  }
+  a_sum = s;
+  b_max = mx;
+  __syncthreads();
+  if (tid == 0) S->sseq = seq;
+}
+
 inline bool set_args(const PcgArgs& a_in, cudaStream_t st) {
   // Between two termination checks consecutive solves of an ADMM run have identical argument
   // blocks (same vectors, same rho, prim_res / dual_res refreshed only at the checks; admm_iter is
@@ -356,7 +413,7 @@ __global__ void __launch_bounds__(kBlock) g_rhs_norm_sum(int slot, PcgRun* run, 
 // row-sharded P2 tail: r = Kp - b1 ; p = -M^-1 r ; totals r'y, ||r||_inf (n-vectors are replicated,
 // so every rank computes the same totals and no scalar exchange is needed)
 __global__ void __launch_bounds__(kBlock) g_resid_init(int slot, PcgRun* run, double* red,
-                                                       int stride, int off) {
+                                                       int stride, int off, int p2p) {
   __shared__ double shr[33];
   const PcgArgs& a = c_args[slot];
   double acc0 = 0.0, acc1 = 0.0;
@@ -375,12 +432,81 @@ __global__ void __launch_bounds__(kBlock) g_resid_init(int slot, PcgRun* run, do
   double tot;
   publish<true>(acc1, red, stride, SLOT_RMAX, nullptr, false, shr, tot);
   if (publish<false>(acc0, red, stride, SLOT_RTY, &run->ticket[SLOT_RTY], true, shr, tot)) {
-    const double rmax = fold<true>(red, stride, SLOT_RMAX, shr);
+    double rmax = fold<true>(red, stride, SLOT_RMAX, shr);
+    if (p2p) xchg_scalars(tot, rmax, tot, rmax);     // peer-memory exchange of (r'y, ||r||_inf)
     if (threadIdx.x == 0) {
       run->rTy = tot;
       run->rnorm = rmax;
       run->ticket[SLOT_RTY] = 0;
     }
+  }
+}
+
+// row-sharded, peer-memory path: push the n_shared-long head of this rank's partial K p (MODE 1: and the
+// three dot-product partials over the columns it owns) into every peer's exchange buffer, wait for the
+// peers' pushes, fold the heads in rank order into Kp, and (MODE 1) finish the three dots -- the shared
+// columns are counted here, identically on every rank -- and with them alpha and beta.  One kernel:
+// the transfer over NVLink overlaps the tail of the pushing CTAs, nothing returns to the host.
+// The grid must be co-resident (CTAs spin on the peers' sequence words): <= one CTA per SM.
+template <int MODE>
+__global__ void __launch_bounds__(kBlock) g_xchg_vector(int slot, PcgRun* run, double* red, int stride) {
+  __shared__ double shr[48];
+  __shared__ int s_lastx;
+  const PcgArgs& a = c_args[slot];
+  const XchgView& X = c_xchg;
+  XchgState* S = X.state;
+  const int ns = a.n_shared, me = X.rank, world = X.world;
+  const unsigned long long seq = *(volatile unsigned long long*)&S->vseq + 1;
+  const int set = (int)(seq & 1ull);
+  const int gtid = blockIdx.x * blockDim.x + threadIdx.x, gstride = gridDim.x * blockDim.x;
+  T* __restrict__ Kp = a.Kp;
+  for (int q = 0; q < world; q++) {
+    if (q == me) continue;
+    double* dst = X.peer[q] + xchg_vec(set, me);
+    for (int i = gtid; i < ns; i += gstride) dst[i] = (double)Kp[i];
+    if (MODE == 1 && gtid < 3) dst[ns + gtid] = run->dots[gtid];
+  }
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) s_lastx = (atomicAdd(&S->ticket, 1u) == gridDim.x - 1);
+  __syncthreads();
+  if (s_lastx) {           // every CTA of this rank has pushed (and fenced): publish the sequence number
+    __threadfence_system();
+    if ((int)threadIdx.x < world && (int)threadIdx.x != me)
+      st_release_sys((unsigned long long*)(X.peer[threadIdx.x] + xchg_vflag(set, me)), seq);
+    if (threadIdx.x == 0) S->ticket = 0;
+  }
+  if ((int)threadIdx.x < world && (int)threadIdx.x != me) {
+    if (!xchg_wait((const unsigned long long*)(X.mine + xchg_vflag(set, threadIdx.x)), seq)) S->err = 1;
+  }
+  __syncthreads();
+  double acc0 = 0.0, acc1 = 0.0, acc2 = 0.0;
+  for (int i = gtid; i < ns; i += gstride) {
+    double sum = 0.0;
+    for (int r = 0; r < world; r++) sum += (r == me) ? (double)Kp[i] : __ldcg(X.mine + xchg_vec(set, r) + i);
+    const T kp = (T)sum;
+    Kp[i] = kp;
+    if (MODE == 1) {
+      const T yk = a.minv[i] * kp;
+      acc0 += (double)a.p[i] * (double)kp;
+      acc1 += (double)a.r[i] * (double)yk;
+      acc2 += (double)kp * (double)yk;
+    }
+  }
+  block_sum3(acc0, acc1, acc2, shr);
+  const double part[3] = {acc0, acc1, acc2};
+  const int slots[3] = {SLOT_PKP, SLOT_RKP, SLOT_KPKP};
+  double tot[3];
+  if (publish_fold<3, false>(part, slots, red, stride, &S->ticket2, shr, tot) && threadIdx.x == 0) {
+    if (MODE == 1) {
+      for (int r = 0; r < world; r++)
+        for (int j = 0; j < 3; j++)
+          tot[j] += (r == me) ? run->dots[j] : __ldcg(X.mine + xchg_vec(set, r) + ns + j);
+      run->pKp = tot[0];
+      cg_step_scalars(run, tot[0], tot[1], tot[2]);
+    }
+    S->ticket2 = 0;
+    S->vseq = seq;
   }
 }
 
@@ -449,6 +575,8 @@ __global__ void g_step_scalars(PcgRun* run) {
 //   MODE 3: P1   Ax = A x ; t = rho .* (Ax - b2)       (exact recomputation of the carried product)
 //   MODE 4: Kp = A' t   MODE 5: Kp = K2 [p; t]   MODE 6: Kp = K2 [x; t]   (plain stores: the row-sharded
 //           driver exchanges the partial Kp before any scalar is formed; also the phase profile)
+//   MODE 7: Kp = K2 [p; t] and the three dot partials over the rows >= n_shared (the columns this rank
+//           OWNS, complete without any exchange) -> run->dots  (row-sharded peer-memory path)
 constexpr int kLeanBlock = 512;
 constexpr int kLeanCtasPerSm = 3;
 static_assert(kTile == 4 * kLeanBlock, "lean pass assumes one batch of 4 per thread");
@@ -468,7 +596,8 @@ __global__ void __launch_bounds__(kLeanBlock, kLeanCtasPerSm) g_lean_pass(int sl
   const T* __restrict__   val     = M.val;
   const int4* __restrict__ desc   = M.desc;
   const int nblocks = M.nblocks;
-  const T* __restrict__ src = (MODE == 4) ? a.t : ((MODE == 0 || MODE == 1 || MODE == 5) ? a.p : a.x);   // 2, 3, 6: x
+  const T* __restrict__ src = (MODE == 4) ? a.t : ((MODE == 0 || MODE == 1 || MODE == 5 || MODE == 7) ? a.p : a.x);   // 2, 3, 6: x
+  const int n_shared = a.n_shared;
   const T* __restrict__ t = a.t;
   const int n = a.n;
   const int tid = threadIdx.x;
@@ -513,6 +642,14 @@ __global__ void __launch_bounds__(kLeanBlock, kLeanCtasPerSm) g_lean_pass(int sl
         } else if (MODE == 3) {
           a.Ax[row] = sum;
           a.t[row]  = (a.rho_vec ? a.rho_vec[row] : a.rho) * (sum - a.b[n + row]);
+        } else if (MODE == 7) {
+          a.Kp[row] = sum;
+          if (row >= n_shared) {
+            const T yk = a.minv[row] * sum;
+            acc  += (double)src[row] * (double)sum;
+            acc1 += (double)a.r[row] * (double)yk;
+            acc2 += (double)sum * (double)yk;
+          }
         } else if (MODE >= 4) {
           a.Kp[row] = sum;
         } else if (MODE == 1) {
@@ -543,6 +680,17 @@ __global__ void __launch_bounds__(kLeanBlock, kLeanCtasPerSm) g_lean_pass(int sl
     if (publish_fold<3, false>(part, slots, red, stride, &run->ticket[SLOT_PKP], shr, tot) && tid == 0) {
       run->pKp = tot[0];
       cg_step_scalars(run, tot[0], tot[1], tot[2]);
+      run->ticket[SLOT_PKP] = 0;
+    }
+  } else if (MODE == 7) {
+    block_sum3(acc, acc1, acc2, shr);
+    const double part[3] = {acc, acc1, acc2};
+    const int slots[3] = {SLOT_PKP, SLOT_RKP, SLOT_KPKP};
+    double tot[3];
+    if (publish_fold<3, false>(part, slots, red, stride, &run->ticket[SLOT_PKP], shr, tot) && tid == 0) {
+      run->dots[0] = tot[0];
+      run->dots[1] = tot[1];
+      run->dots[2] = tot[2];
       run->ticket[SLOT_PKP] = 0;
     }
   } else if (MODE == 2) {
@@ -584,7 +732,7 @@ __global__ void g_loop_init(int slot, PcgRun* run, cudaGraphConditionalHandle h)
 // L3+L4 in one kernel (graph driver): x += a p ; r += a Kp ; p = beta p - M^-1 r ; Ax += a w ;
 // totals r'y (exact), ||r||_inf ; last CTA: it++, loop condition.  8 n F + 3 m F bytes.
 __global__ void __launch_bounds__(kBlock) g_update_fused(int slot, PcgRun* run, double* red, int stride,
-                                                         cudaGraphConditionalHandle h, int off) {
+                                                         cudaGraphConditionalHandle h, int off, int p2p) {
   __shared__ double shr[33];
   const PcgArgs& a = c_args[slot];
   const int n = a.n, m = a.m;
@@ -612,7 +760,8 @@ __global__ void __launch_bounds__(kBlock) g_update_fused(int slot, PcgRun* run, 
   double tot;
   publish<true>(acc_max, red, stride, SLOT_RMAX, nullptr, false, shr, tot);
   if (publish<false>(acc_rty, red, stride, SLOT_RTY, &run->ticket[SLOT_RTY], true, shr, tot)) {
-    const double rmax = fold<true>(red, stride, SLOT_RMAX, shr);
+    double rmax = fold<true>(red, stride, SLOT_RMAX, shr);
+    if (p2p) xchg_scalars(tot, rmax, tot, rmax);     // row-sharded: (r'y, ||r||_inf) of all ranks, over NVLink
     if (threadIdx.x == 0) {
       run->rTy   = tot;
       run->rnorm = rmax;
@@ -644,6 +793,14 @@ __global__ void __launch_bounds__(kBlock) g_epilogue(int slot, PcgRun* run) {
     o.n_solves        += 1;
     *a.st = o;
   }
+}
+
+// grid of the exchange kernel: its CTAs spin on the peers' sequence words, so all of them must be
+// resident at once -- at most one per SM
+inline int xchg_grid(int n_shared) {
+  int g = (n_shared + kBlock * 2 - 1) / (kBlock * 2);
+  if (g > ctx().sm_count) g = ctx().sm_count;
+  return g > 0 ? g : 1;
 }
 
 // one wave of co-resident CTAs looping over the tiles (see the note on per-CTA tails above)
@@ -695,7 +852,35 @@ int b200_pcg_graph_build(b200_pcg* s) {
   if (getenv("B200_TRACE_SETUP"))
     fprintf(stderr, "[b200 trace] graph PCG driver: %s passes, K2 tiles %d, A tiles %d, partial stride %d\n",
             lean ? "lean" : "generic", s->K2.nblocks, s->m > 0 ? s->A->nblocks : 0, s->gred_stride);
-  if (s->sharded) return 0;   // host-driven loop with an all-reduce per iteration: no graph
+  // Row-sharded solve.  With the peer-memory exchange (NVLink P2P stores inside the kernels, dist.cu) the
+  // loop stays a CUDA-graph WHILE node: A pass, operator pass with the owned-column dots, ONE exchange
+  // kernel (vector head + dots -> alpha, beta), fused update whose last CTA trades (r'y, ||r||_inf) with
+  // the peers and sets the loop condition.  Otherwise (no P2P, plain row layout, over-long rows, head
+  // larger than an exchange slot): host-driven loop with NCCL all-reduces.
+  bool p2p = s->sharded && lean && dist_p2p_ready() && dist_split() && getenv("B200_DIST_NO_P2P") == nullptr &&
+             dist_n_shared() + 8 <= kXchgCap && s->m > 0;
+  if (s->sharded) {
+    // the ranks must agree (a rank whose shard has an over-long row cannot take the lean path): one
+    // MAX all-reduce of "I cannot" at solver creation, which every rank reaches in lockstep
+    double veto = p2p ? 0.0 : 1.0;
+    double* d_veto = reinterpret_cast<double*>(s->d_run);     // scratch: zeroed again below
+    ok &= B200_CHECK(cudaMemcpyAsync(d_veto, &veto, sizeof(double), cudaMemcpyHostToDevice, c.stream));
+    dist_allreduce_f64(d_veto, 1, true);
+    ok &= B200_CHECK(cudaMemcpyAsync(&veto, d_veto, sizeof(double), cudaMemcpyDeviceToHost, c.stream));
+    ok &= B200_CHECK(cudaStreamSynchronize(c.stream));
+    ok &= B200_CHECK(cudaMemsetAsync(s->d_run, 0, sizeof(PcgRun), c.stream));
+    if (!ok) return 1;
+    p2p = p2p && veto == 0.0;
+  }
+  s->p2p = p2p ? 1 : 0;
+  if (s->sharded && !p2p) return 0;
+  if (p2p) {
+    const XchgView v = dist_xchg_view();
+    if (!B200_CHECK(cudaMemcpyToSymbolAsync(c_xchg, &v, sizeof(v), 0, cudaMemcpyHostToDevice, c.stream))) return 1;
+    if (!B200_CHECK(cudaStreamSynchronize(c.stream))) return 1;
+  }
+  const int x_off = p2p ? dist_col_off() : 0;
+  const int x_p2p = p2p ? 1 : 0;
 
   cudaGraph_t g = nullptr;
   if (!B200_CHECK(cudaGraphCreate(&g, 0))) return 1;
@@ -749,13 +934,16 @@ int b200_pcg_graph_build(b200_pcg* s) {
   }
   {
     void* a2[] = {(void*)&d_args, (void*)&d_run, (void*)&d_red, (void*)&stride};
-    if (lean) add((void*)g_lean_pass<1>, dim3(lean_grid(s->K2)), dim3(kLeanBlock), 0, a2);
+    if (p2p) {
+      add((void*)g_lean_pass<7>, dim3(lean_grid(s->K2)), dim3(kLeanBlock), 0, a2);
+      add((void*)g_xchg_vector<1>, dim3(xchg_grid(dist_n_shared())), dim3(kBlock), 0, a2);
+    } else if (lean) add((void*)g_lean_pass<1>, dim3(lean_grid(s->K2)), dim3(kLeanBlock), 0, a2);
     else add((void*)g_pass_K<1>, dim3(pass_grid(s->K2, cap)), dim3(kSpmvBlock), kSpmvSmemBytes, a2);
   }
   {
     // L3 + L4 in one kernel: alpha AND beta are known after the fused-operator pass
-    int zero_off = 0;
-    void* a3[] = {(void*)&d_args, (void*)&d_run, (void*)&d_red, (void*)&stride, (void*)&h, (void*)&zero_off};
+    int zero_off = x_off, use_p2p = x_p2p;
+    void* a3[] = {(void*)&d_args, (void*)&d_run, (void*)&d_red, (void*)&stride, (void*)&h, (void*)&zero_off, (void*)&use_p2p};
     int nm = s->n > s->m ? s->n : s->m;
     int gu = ew_grid(nm) < cap ? ew_grid(nm) : cap;
     add((void*)g_update_fused, dim3(gu), dim3(kBlock), 0, a3);
@@ -827,7 +1015,7 @@ int b200_pcg_graph_solve(b200_pcg* s, const PcgArgs& a) {
       if (s->lean) g_lean_pass<1><<<lean_grid(s->K2), kLeanBlock, 0, st>>>(d_args, s->d_run, s->d_gred, cap);
       else g_pass_K<1><<<pass_grid(s->K2, cap), kSpmvBlock, kSpmvSmemBytes, st>>>(d_args, s->d_run, s->d_gred, cap);
       count_launch("L2 pass K2");
-      g_update_fused<<<gu, kBlock, 0, st>>>(d_args, s->d_run, s->d_gred, cap, none, 0);
+      g_update_fused<<<gu, kBlock, 0, st>>>(d_args, s->d_run, s->d_gred, cap, none, 0, 0);
       count_launch("L3+L4 update");
     }
   } else {
@@ -916,7 +1104,7 @@ int b200_pcg_sharded_solve(b200_pcg* s, const PcgArgs& a) {
   else g_pass_K<2><<<pass_grid(s->K2, cap), kSpmvBlock, kSpmvSmemBytes, st>>>(d_args, run, s->d_gred, cap);
   count_launch("g_p1_carried");
   exchange_vector(s->d_Kp, n);
-  g_resid_init<<<gn, kBlock, 0, st>>>(d_args, run, s->d_gred, cap, off);
+  g_resid_init<<<gn, kBlock, 0, st>>>(d_args, run, s->d_gred, cap, off, 0);
   count_launch("g_resid_init");
   exchange_residual_scalars(run, st);
 
@@ -943,7 +1131,7 @@ int b200_pcg_sharded_solve(b200_pcg* s, const PcgArgs& a) {
     exchange_scalars(run->dots, 3, false);
     g_step_scalars<<<1, 32, 0, st>>>(run);
     count_launch("g_step_scalars");
-    g_update_fused<<<gu, kBlock, 0, st>>>(d_args, run, s->d_gred, cap, none, off);
+    g_update_fused<<<gu, kBlock, 0, st>>>(d_args, run, s->d_gred, cap, none, off, 0);
     count_launch("g_update_fused");
     exchange_residual_scalars(run, st);
   }
@@ -967,7 +1155,7 @@ void b200_pcg_profile_register(b200_pcg* s, bool alive) {
 
 extern "C" int b200_pcg_profile_last(int reps, double* out_us, int nout) {
   b200_pcg* s = g_profile_target;
-  if (!s || !s->d_args || !s->lean || s->sharded || nout < 12) return -1;
+  if (!s || !s->d_args || !s->lean || nout < 12) return -1;   // sharded: the passes of this rank, no exchange
   Context& c = ctx();
   cudaStream_t st = c.stream;
   const int cap = s->gred_stride;
@@ -991,7 +1179,7 @@ extern "C" int b200_pcg_profile_last(int reps, double* out_us, int nout) {
   };
   auto passA  = [&] { if (m > 0) g_lean_pass<0><<<lean_grid(*s->A, false), kLeanBlock, 0, st>>>(d_args, run, red, cap); };
   auto passK  = [&] { g_lean_pass<1><<<lean_grid(s->K2), kLeanBlock, 0, st>>>(d_args, run, red, cap); };
-  auto upd    = [&] { g_update_fused<<<gu, kBlock, 0, st>>>(d_args, run, red, cap, none, 0); };
+  auto upd    = [&] { g_update_fused<<<gu, kBlock, 0, st>>>(d_args, run, red, cap, none, 0, 0); };
   out_us[0]  = timeit(passA);
   out_us[1]  = timeit(passK);
   out_us[2]  = timeit(upd);

@@ -248,7 +248,32 @@ def init_sharded(dist, local_rank, precision="f64"):
     uid = exchange_unique_id(make_id, dist)
     if k.b200_dist_init(dist.get_rank(), dist.get_world_size(), uid) != 0:
         raise RuntimeError("ncclCommInitRank failed")
+    enable_peer_exchange(k, dist)
     return k
+
+
+def enable_peer_exchange(k, dist):
+    """Peer-memory exchange for the CG loop (csrc/dist.cu): every rank exports the CUDA IPC handle of its
+    exchange buffer, the 64-byte handles are all-gathered in rank order and imported.  Returns True when
+    every rank succeeded; otherwise the sharded solve keeps its NCCL path (also with B200_DIST_NO_P2P=1)."""
+    import os
+    world = dist.get_world_size()
+    if world < 2 or world > 8 or os.environ.get("B200_DIST_NO_P2P"):
+        return False
+    k.b200_dist_p2p_export.argtypes = [C.c_char_p]
+    k.b200_dist_p2p_export.restype = C.c_int
+    k.b200_dist_p2p_import.argtypes = [C.c_char_p, C.c_int]
+    k.b200_dist_p2p_import.restype = C.c_int
+    raw = C.create_string_buffer(64)
+    rc = k.b200_dist_p2p_export(raw)
+    got = [None] * world
+    dist.all_gather_object(got, (int(rc), raw.raw))
+    if any(r != 0 for r, _ in got):
+        return False
+    rc = k.b200_dist_p2p_import(b"".join(h for _, h in got), world)
+    oks = [None] * world
+    dist.all_gather_object(oks, int(rc))
+    return all(o == 0 for o in oks)
 
 
 class ShardedOSQP(OSQP):
@@ -269,7 +294,39 @@ class ShardedOSQP(OSQP):
         self._lib.osqp_b200_dist_configure_split.argtypes = [C.c_int] * 4
         self._lib.osqp_b200_dist_configure_split.restype = C.c_int
 
+    @staticmethod
+    def _check_settings(settings):
+        """Every rank must take the same host-side decisions: options whose control flow depends on a
+        rank-local clock or that run kernels over vectors of other lengths are refused."""
+        if settings.get("polishing", 0):
+            raise ValueError("polishing is not supported in the row-sharded mode")
+        if settings.get("time_limit", 0):
+            raise ValueError("time_limit makes ranks stop at different iterations: not supported when sharded")
+        if settings.get("adaptive_rho", 1) not in (0, 1):
+            raise ValueError("row-sharded mode needs adaptive_rho in {0 (off), 1 (iteration based)}")
+
+    def setup_local(self, shard, n_global, m_global, **settings):
+        """Set up from data that is ALREADY sharded: `shard` is this rank's QP in the column-split layout
+        (dict P, q, A, l, u, n_shared as produced by shard_problem_split or problems.*_shard): columns
+        [the n_shared columns touched by several ranks ; the columns only this rank touches], its rows
+        of A.  No rank ever sees the whole problem."""
+        self._check_settings(settings)
+        self.n_global, self.m_global = int(n_global), int(m_global)
+        A = sp.csc_matrix(shard["A"])
+        l, u = np.asarray(shard["l"], dtype=float), np.asarray(shard["u"], dtype=float)
+        self.padded = 0
+        if A.shape[0] == A.shape[1]:        # the backend tells row vectors from column vectors by length
+            A = sp.vstack([A, sp.csc_matrix((1, A.shape[1]))], format="csc")
+            l, u = np.append(l, -np.inf), np.append(u, np.inf)
+            self.padded = 1
+        self.n_shared = int(shard["n_shared"])
+        rc = self._lib.osqp_b200_dist_configure_split(A.shape[1], A.shape[0], self.n_shared, self.n_global)
+        if rc != 0:
+            raise ValueError("invalid column-split layout for this rank")
+        return OSQP.setup(self, shard["P"], shard["q"], A, l, u, **settings)
+
     def setup(self, P, q, A, l, u, **settings):
+        self._check_settings(settings)
         pb = dict(P=P, q=q, A=A, l=l, u=u)
         self.n_global, self.m_global = sp.csc_matrix(P).shape[0], sp.csc_matrix(A).shape[0]
         if self.layout == "split":

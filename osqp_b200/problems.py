@@ -188,3 +188,139 @@ def nnz_P_full(P):
     coo = Pu.tocoo()
     ndiag = int((coo.row == coo.col).sum())
     return 2 * (Pu.nnz - ndiag) + P.shape[0]
+
+
+# ------------------------------------------------------------------------------------------------
+# Block-seeded generators for the row-sharded mode (BASELINE configs[3]): the data matrix is defined
+# as a stack of sample blocks, each drawn from its own seeded stream, so that the GLOBAL problem does
+# not depend on the number of ranks and a rank can generate just the samples it owns -- no rank ever
+# builds (or slices) the whole 1e8-nnz problem.  `*_shard(rank, world, ...)` returns the rank's QP in the
+# column-split layout of osqp_b200.dist (columns = [features, shared by all ranks ; the slack columns
+# of the rank's samples]), plus the global ids of its rows and columns; world = 1 gives the whole QP in
+# the variable order of the docs example.
+
+SAMPLE_BLOCK = 1 << 15
+
+
+def _owned_blocks(n_samples, rank, world, block=SAMPLE_BLOCK):
+    nb = -(-n_samples // block)
+    j0, j1 = (rank * nb) // world, ((rank + 1) * nb) // world
+    return [(j, j * block, min((j + 1) * block, n_samples)) for j in range(j0, j1)]
+
+
+def _data_rows(n_features, blocks, density, seed, s0):
+    """Entries of the rows [s0, s1) of the data matrix as (key-sorted) CSC pieces: returns (col, row -
+    s0, value) sorted by column then row, duplicates removed, one independent stream per sample block."""
+    keys, vals = [], []
+    m_loc = blocks[-1][2] - s0 if blocks else 0
+    for j, b0, b1 in blocks:
+        rng = np.random.default_rng([seed, 7919, j])
+        cnt = int(round(density * (b1 - b0) * n_features))
+        rows = rng.integers(0, b1 - b0, size=cnt, dtype=np.int64) + (b0 - s0)
+        cols = rng.integers(0, n_features, size=cnt, dtype=np.int64)
+        key = np.unique(cols * m_loc + rows)
+        keys.append(key)
+        vals.append(rng.random(key.size))
+    if not keys:
+        return np.zeros(0, np.int64), np.zeros(0, np.int64), np.zeros(0)
+    key, val = np.concatenate(keys), np.concatenate(vals)
+    o = np.argsort(key, kind="stable")          # blocks cover disjoint rows: keys are unique
+    key, val = key[o], val[o]
+    return key // m_loc, key % m_loc, val
+
+
+def _csc_with_slacks(n_features, m_loc, col, row, val, slack_blocks):
+    """CSC of [B | S_1 | S_2 ...] stacked over row blocks: B = (col, row, val) sorted by column, and each
+    slack block k is a list of (row_offset, value) pairs giving the entries of slack column i at rows
+    row_offset + i.  Built directly from index arithmetic (no bmat / COO round trip)."""
+    nnzB = col.size
+    indptr = [np.concatenate([[0], np.cumsum(np.bincount(col, minlength=n_features))])]
+    indices, data = [row], [val]
+    base = nnzB
+    for entries in slack_blocks:
+        k = len(entries)
+        ii = np.arange(m_loc, dtype=np.int64)
+        idx = np.empty((m_loc, k), dtype=np.int64)
+        dat = np.empty((m_loc, k))
+        for t, (off, v) in enumerate(sorted(entries)):
+            idx[:, t] = off + ii
+            dat[:, t] = v
+        indices.append(idx.ravel())
+        data.append(dat.ravel())
+        indptr.append(base + k * (ii + 1))
+        base += k * m_loc
+    nrows = max(off for entries in slack_blocks for off, _ in entries) + m_loc if slack_blocks else m_loc
+    ncols = n_features + m_loc * len(slack_blocks)
+    A = sp.csc_matrix((np.concatenate(data), np.concatenate(indices).astype(np.int32),
+                       np.concatenate(indptr).astype(np.int32)), shape=(nrows, ncols))
+    A.has_sorted_indices = True
+    return A
+
+
+def svm_shard(rank, world, n_features=10_000, n_samples=10_000_000, density=1e-3, gamma=1.0, seed=1,
+              block=SAMPLE_BLOCK):
+    """docs/examples/svm.rst:37-57, variables (x, t); samples [s0, s1) of rank `rank`."""
+    n, m = n_features, 2 * (n_samples // 2)
+    N = m // 2
+    blocks = _owned_blocks(m, rank, world, block)
+    s0, s1 = blocks[0][1], blocks[-1][2]
+    mS = s1 - s0
+    col, row, val = _data_rows(n, blocks, density, seed, s0)
+    b = np.where(np.arange(s0, s1) < N, 1.0, -1.0)
+    # Ad = A / sqrt(n) +- (A != 0) / n ; constraint rows diag(b) Ad
+    val = b[row] * (val / np.sqrt(n) + b[row] / n)
+    A = _csc_with_slacks(n, mS, col, row, val, [[(0, -1.0), (mS, 1.0)]])
+    P = sp.block_diag([sp.eye(n), sp.csc_matrix((mS, mS))], format="csc")
+    q = np.hstack([np.zeros(n), gamma * np.ones(mS)])
+    l = np.hstack([-np.inf * np.ones(mS), np.zeros(mS)])
+    u = np.hstack([-np.ones(mS), np.inf * np.ones(mS)])
+    cols = np.concatenate([np.arange(n), n + np.arange(s0, s1)])
+    rows = np.concatenate([np.arange(s0, s1), m + np.arange(s0, s1)])
+    return dict(P=P, q=q, A=A, l=l, u=u, n_shared=n, cols=cols, rows=rows, n_global=n + m, m_global=2 * m,
+                name=f"svm_n{n}_m{m}_shard{rank}of{world}")
+
+
+def huber_shard(rank, world, n_features=10_000, n_samples=10_000_000, density=1e-3, seed=1, block=SAMPLE_BLOCK):
+    """docs/examples/huber.rst:44-63, variables (x, u, r, s); samples [s0, s1) of rank `rank`."""
+    n, m = n_features, n_samples
+    blocks = _owned_blocks(m, rank, world, block)
+    s0, s1 = blocks[0][1], blocks[-1][2]
+    mS = s1 - s0
+    col, row, val = _data_rows(n, blocks, density, seed, s0)
+    x_true = np.random.default_rng([seed, 104729]).standard_normal(n) / np.sqrt(n)
+    b = np.bincount(row, weights=val * x_true[col], minlength=mS)
+    for j, b0, b1 in blocks:
+        rng = np.random.default_rng([seed, 15485863, j])
+        ind95 = (rng.random(b1 - b0) < 0.95).astype(float)
+        b[b0 - s0:b1 - s0] += 0.5 * rng.standard_normal(b1 - b0) * ind95 + 10.0 * rng.random(b1 - b0) * (1.0 - ind95)
+    # A = [Ad -I -I I; 0 0 I 0; 0 0 0 I] restricted to the rank's samples
+    A = _csc_with_slacks(n, mS, col, row, val, [[(0, -1.0)], [(0, -1.0), (mS, 1.0)], [(0, 1.0), (2 * mS, 1.0)]])
+    P = sp.block_diag([sp.csc_matrix((n, n)), 2 * sp.eye(mS), sp.csc_matrix((2 * mS, 2 * mS))], format="csc")
+    q = np.append(np.zeros(mS + n), 2 * np.ones(2 * mS))
+    l = np.hstack([b, np.zeros(2 * mS)])
+    u = np.hstack([b, np.inf * np.ones(2 * mS)])
+    S = np.arange(s0, s1)
+    cols = np.concatenate([np.arange(n), n + S, n + m + S, n + 2 * m + S])
+    rows = np.concatenate([S, m + S, 2 * m + S])
+    return dict(P=P, q=q, A=A, l=l, u=u, n_shared=n, cols=cols, rows=rows, n_global=n + 3 * m, m_global=3 * m,
+                name=f"huber_n{n}_m{m}_shard{rank}of{world}")
+
+
+def assemble_shards(shards):
+    """The global QP from the shards of all ranks (tests / small sizes only)."""
+    n, m = shards[0]["n_global"], shards[0]["m_global"]
+    ns = shards[0]["n_shared"]
+    A = sp.lil_matrix((m, n))
+    P = sp.lil_matrix((n, n))
+    q, l, u = np.zeros(n), np.zeros(m), np.zeros(m)
+    for sh in shards:
+        Ac = sp.coo_matrix(sh["A"])
+        A = A + sp.coo_matrix((Ac.data, (sh["rows"][Ac.row], sh["cols"][Ac.col])), shape=(m, n))
+        Pc = sp.coo_matrix(sh["P"])
+        own = (Pc.row >= ns) | (Pc.col >= ns)
+        first = sh is shards[0]
+        keep = own | first                          # the shared block of P is the same on every rank
+        P = P + sp.coo_matrix((Pc.data[keep], (sh["cols"][Pc.row[keep]], sh["cols"][Pc.col[keep]])), shape=(n, n))
+        q[sh["cols"]] = sh["q"]
+        l[sh["rows"]], u[sh["rows"]] = sh["l"], sh["u"]
+    return dict(P=sp.csc_matrix(P), q=q, A=sp.csc_matrix(A), l=l, u=u)

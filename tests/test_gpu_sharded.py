@@ -21,19 +21,45 @@ def _ngpus():
         return 0
 
 
-@pytest.mark.skipif(_ngpus() < 2, reason="needs 2 GPUs")
-@pytest.mark.parametrize("layout", ["split", "rows"])
-@pytest.mark.parametrize("family", ["lasso", "portfolio", "huber", "svm"])
-def test_two_rank_sharded_solve_matches_oracle(family, layout):
+def _run_worker(extra, env_extra=None):
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
-           "--master-addr", "127.0.0.1", "--master-port", "29541", str(ROOT / "tools" / "sharded_worker.py"),
-           "--family", family, "--scale", "0.003", "--check", "--layout", layout]
-    out = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=dict(os.environ, MASTER_ADDR="127.0.0.1"))
+           "--master-addr", "127.0.0.1", "--master-port", "29541", str(ROOT / "tools" / "sharded_worker.py")] + extra
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1")
+    env.update(env_extra or {})
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=env)
     line = [l for l in out.stdout.splitlines() if l.startswith("SHARDED ")]
     assert line, out.stdout[-1500:] + out.stderr[-1500:]
-    res = json.loads(line[0][len("SHARDED "):])
+    return json.loads(line[0][len("SHARDED "):]), out
+
+
+@pytest.mark.skipif(_ngpus() < 2, reason="needs 2 GPUs")
+@pytest.mark.parametrize("exchange", ["p2p", "nccl"])
+@pytest.mark.parametrize("layout", ["split", "rows"])
+@pytest.mark.parametrize("family", ["lasso", "portfolio", "huber", "svm"])
+def test_two_rank_sharded_solve_matches_oracle(family, layout, exchange):
+    """exchange = p2p: peer-memory exchange inside the kernels, CG loop as a CUDA graph (column-split layout
+    of matrices without over-long rows); nccl: host-driven loop with NCCL all-reduces (B200_DIST_NO_P2P)."""
+    if exchange == "p2p" and layout == "rows":
+        pytest.skip("plain row blocks keep the NCCL path")
+    res, out = _run_worker(["--family", family, "--scale", "0.003", "--check", "--layout", layout],
+                           {"B200_DIST_NO_P2P": "1"} if exchange == "nccl" else None)
     assert res["PARITY"] == "OK", res
-    assert res["allreduce_calls"] > res["cg_iters"]          # one exchange per K.p (+ residual checks)
+    if exchange == "p2p" and family != "portfolio":          # portfolio: the dense budget row is an over-long row
+        assert res["p2p"] is True
+        assert res["allreduce_calls"] < res["cg_iters"], res    # no collective inside the CG loop
+    else:
+        assert res["allreduce_calls"] > res["cg_iters"]          # one exchange per K.p (+ residual checks)
     if layout == "split" and family != "portfolio":         # epigraph families: only the features are shared
         assert res["n_shared"] < 0.2 * res["n"], res
+    assert "REPLICATED_X_IDENTICAL True" in out.stdout
+
+
+@pytest.mark.skipif(_ngpus() < 2, reason="needs 2 GPUs")
+@pytest.mark.parametrize("family", ["svm", "huber"])
+def test_two_rank_block_seeded_shards_match_oracle(family):
+    """bench.py's sharded path: every rank generates only its sample blocks and sets up through
+    ShardedOSQP.setup_local; the assembled solution matches the oracle on the assembled global QP."""
+    res, out = _run_worker(["--family", family, "--scale", "0.003", "--check", "--blocks"])
+    assert res["PARITY"] == "OK" and res["blocks"] is True, res
+    assert res["p2p"] is True and res["allreduce_calls"] < res["cg_iters"], res
     assert "REPLICATED_X_IDENTICAL True" in out.stdout
