@@ -21,7 +21,7 @@ CFLAGS  := -O3 -fPIC -std=gnu11 -w -DNDEBUG
 CINC    := -Ialgebra/b200/config -Ialgebra/b200 -Iinclude \
            -I$(REF)/include/public -I$(REF)/include/private
 
-CU_SRC   := $(CSRC)/context.cu $(CSRC)/vec_kernels.cu $(CSRC)/csr.cu $(CSRC)/transpose.cu $(CSRC)/pcg.cu $(CSRC)/pcg_graph.cu $(CSRC)/dist.cu
+CU_SRC   := $(CSRC)/context.cu $(CSRC)/vec_kernels.cu $(CSRC)/csr.cu $(CSRC)/transpose.cu $(CSRC)/pcg.cu $(CSRC)/pcg_graph.cu $(CSRC)/dist.cu $(CSRC)/batch.cu
 CU_HDR   := $(CSRC)/common.cuh $(CSRC)/csr.cuh $(CSRC)/pcg.cuh include/osqp_b200.h
 CORE_SRC := $(addprefix $(REF)/src/,auxil.c error.c scaling.c util.c osqp_api.c polish.c timing_linux.c)
 ALG_SRC  := $(wildcard algebra/b200/*.c)

@@ -257,6 +257,32 @@ void b200_admm_residuals(const b200_float* d_x, const b200_float* d_y, const b20
                          const b200_float* d_q, const b200_float* d_l, const b200_float* d_u,
                          const b200_float* d_Einv, const b200_float* d_Dinv, b200_float infval,
                          b200_float deadzone, int n, int m, double* h_out);
+/* ------------------------------------------------------ batches of small QPs (BASELINE configs[4])
+ * nb independent QPs that share P and A (hence the scaling D, E, c of the set-up template problem) and
+ * differ in their bounds (and optionally q): ONE CTA per QP runs the whole osqp_solve loop -- ADMM
+ * steps, reduced-KKT PCG with the reference's tolerance schedule, update_info, check_termination,
+ * adaptive rho -- in shared memory (osqp_b200/csrc/batch.cu cites the reference lines).  Matrices and
+ * scaling vectors are the SCALED device data of the template; d_l_batch / d_u_batch / d_q_batch hold the
+ * users' unscaled values, d_x / d_y receive unscaled solutions.  Status per QP: 1 solved, 2 solved
+ * inaccurate, 7 maximum iterations reached, 9 non-convex (infeasibility certificates are not evaluated
+ * here: unsolved QPs go through the ordinary API).  Returns 0, or 2 (m == 0) / 3 (iterates do not fit
+ * shared memory): use the ordinary API.  Asynchronous on the library stream.
+ * replaces: one osqp_solve per QP = ~100 launches per ADMM iteration through the per-op interface
+ * (include/private/algebra_vector.h:28-290; docs/examples/mpc.rst:30-90 for the workload). */
+typedef struct {
+  b200_float rho, sigma, alpha, eps_abs, eps_rel, adaptive_rho_tolerance;
+  int rho_is_vec, max_iter, check_termination, adaptive_rho, adaptive_rho_interval, check_dualgap,
+      scaled_termination, cg_max_iter, cg_tol_reduction;
+  double cg_tol_fraction;
+} b200_batch_settings;
+int b200_batch_solve(const b200_csr* P, const b200_csr* A, const b200_csr* At, int n, int m, int nb,
+                     const b200_float* d_q, const b200_float* d_q_batch, const b200_float* d_l_batch,
+                     const b200_float* d_u_batch, const b200_float* d_D, const b200_float* d_Dinv,
+                     const b200_float* d_E, const b200_float* d_Einv, b200_float c, b200_float cinv,
+                     const b200_batch_settings* st, b200_float* d_x, b200_float* d_y, int* d_iters, int* d_status,
+                     int* d_cg_iters, int* d_rho_updates, b200_float* d_obj, b200_float* d_prim_res,
+                     b200_float* d_dual_res);
+
 /* ------------------------------------------------------ row-sharded multi-GPU mode
  * One process per GPU.  Every rank holds a block of ROWS of A (and the matching slices of the
  * m-vectors); n-vectors and P are replicated.  The only data-path exchange is one all-reduce of

@@ -1,0 +1,105 @@
+"""Batched small-QP kernel (osqp_b200/csrc/batch.cu, BASELINE configs[4]: MPC QPs n=204, m=360 that share
+P and A): every QP of a batch must agree with (a) a sequential osqp_setup / osqp_solve of the same QP on
+the B200 backend -- same status, objective 1e-6, x 1e-5, iteration count within the stated band -- and
+(b) the CPU oracle (docs/examples/mpc.rst:30-90 generator, seeded x0)."""
+import numpy as np
+import pytest
+
+from osqp_b200 import OSQP, _capi, problems
+from osqp_b200.interface import OSQP as GenericOSQP
+
+pytestmark = pytest.mark.gpu
+
+BENCH = dict(eps_abs=1e-3, eps_rel=1e-3, rho_is_vec=0, adaptive_rho_tolerance=2.0, check_termination=5,
+             polishing=0, verbose=0, warm_starting=0, max_iter=4000)
+TIGHT = dict(eps_abs=1e-6, eps_rel=1e-6, rho_is_vec=0, check_termination=25, polishing=0, verbose=0, max_iter=20000,
+             cg_tol_fraction=1e-8, cg_max_iter=500)
+
+
+def mpc_batch(nb, seed=7):
+    rng = np.random.default_rng(seed)
+    base = problems.mpc(N=12, seed=1)
+    nx = base["nx"]
+    x0s = 0.1 * (2 * rng.random((nb, nx)) - 1)
+    L = np.tile(base["l"], (nb, 1))
+    U = np.tile(base["u"], (nb, 1))
+    L[:, :nx] = -x0s
+    U[:, :nx] = -x0s
+    return base, L, U
+
+
+@pytest.mark.parametrize("settings,rho_is_vec", [(BENCH, 0), (TIGHT, 0), (TIGHT, 1), (BENCH, 1)])
+def test_batch_matches_sequential_solves(b200_lib, settings, rho_is_vec):
+    nb = 24
+    base, L, U = mpc_batch(nb)
+    st = dict(settings, rho_is_vec=rho_is_vec)
+    tmpl = OSQP("f64").setup(base["P"], base["q"], base["A"], base["l"], base["u"], **st)
+    rb = tmpl.solve_batch(L, U)
+    tight = st["eps_abs"] < 1e-4
+    for i in range(nb):
+        s = OSQP("f64").setup(base["P"], base["q"], base["A"], L[i], U[i], **st)
+        r = s.solve()
+        s.cleanup()
+        assert rb.status_val[i] == r.info.status_val == _capi.OSQP_SOLVED, (i, rb.status_val[i], r.info.status)
+        rel = abs(rb.obj_val[i] - r.info.obj_val) / max(1.0, abs(r.info.obj_val))
+        assert rel <= (1e-6 if tight else 5e-3), (i, rb.obj_val[i], r.info.obj_val)
+        if tight:
+            assert np.abs(rb.x[i] - r.x).max() <= 1e-5 * max(1.0, np.abs(r.x).max())
+            assert np.abs(rb.y[i] - r.y).max() <= 1e-4 * max(1.0, np.abs(r.y).max())
+        band = max(0.10 * r.info.iter, 2 * st["check_termination"])
+        assert abs(int(rb.iter[i]) - r.info.iter) <= band, (i, int(rb.iter[i]), r.info.iter)
+    tmpl.cleanup()
+
+
+def test_batch_matches_oracle(b200_lib, oracle_lib):
+    nb = 8
+    base, L, U = mpc_batch(nb, seed=11)
+    kw = {k: v for k, v in TIGHT.items() if not k.startswith("cg_")}
+    tmpl = OSQP("f64").setup(base["P"], base["q"], base["A"], base["l"], base["u"], **TIGHT)
+    rb = tmpl.solve_batch(L, U)
+    for i in range(nb):
+        ro = GenericOSQP(oracle_lib).setup(base["P"], base["q"], base["A"], L[i], U[i], **kw).solve()
+        assert rb.status_val[i] == ro.info.status_val == _capi.OSQP_SOLVED
+        assert abs(rb.obj_val[i] - ro.info.obj_val) <= 1e-6 * max(1.0, abs(ro.info.obj_val))
+        assert np.abs(rb.x[i] - ro.x).max() <= 1e-4 * max(1.0, np.abs(ro.x).max())
+        assert abs(int(rb.iter[i]) - ro.info.iter) <= max(0.10 * ro.info.iter, 50)
+    tmpl.cleanup()
+
+
+def test_batch_with_costs_and_determinism(b200_lib):
+    """per-QP linear costs (same cost scaling as the template) and run-to-run bit-identical results"""
+    nb = 16
+    base, L, U = mpc_batch(nb, seed=3)
+    rng = np.random.default_rng(5)
+    Q = np.tile(base["q"], (nb, 1)) * (1.0 + 0.05 * rng.standard_normal((nb, 1)))
+    tmpl = OSQP("f64").setup(base["P"], base["q"], base["A"], base["l"], base["u"], **TIGHT)
+    r1 = tmpl.solve_batch(L, U, q=Q)
+    r2 = tmpl.solve_batch(L, U, q=Q)
+    assert (r1.x == r2.x).all() and (r1.y == r2.y).all() and (r1.iter == r2.iter).all()
+    for i in range(0, nb, 5):
+        s = OSQP("f64").setup(base["P"], Q[i], base["A"], L[i], U[i], **TIGHT)
+        r = s.solve()
+        s.cleanup()
+        assert r1.status_val[i] == r.info.status_val == _capi.OSQP_SOLVED
+        assert abs(r1.obj_val[i] - r.info.obj_val) <= 1e-5 * max(1.0, abs(r.info.obj_val))
+        assert np.abs(r1.x[i] - r.x).max() <= 1e-4 * max(1.0, np.abs(r.x).max())
+    tmpl.cleanup()
+
+
+def test_batch_larger_than_one_wave(b200_lib):
+    """more QPs than resident CTAs: the persistent loop over QPs; every QP solved and feasible"""
+    nb = 3000
+    base, L, U = mpc_batch(nb, seed=13)
+    tmpl = OSQP("f64").setup(base["P"], base["q"], base["A"], base["l"], base["u"], **BENCH)
+    rb = tmpl.solve_batch(L, U)
+    assert (rb.status_val == _capi.OSQP_SOLVED).all()
+    Ax = rb.x @ base["A"].T.toarray()
+    viol = np.maximum(np.maximum(L - Ax, Ax - U), 0).max()
+    assert viol <= 2e-3 * (1 + np.abs(Ax).max())
+    # a sample of them against sequential solves
+    for i in (0, 1499, 2999):
+        s = OSQP("f64").setup(base["P"], base["q"], base["A"], L[i], U[i], **BENCH)
+        r = s.solve()
+        s.cleanup()
+        assert abs(rb.obj_val[i] - r.info.obj_val) <= 5e-3 * max(1.0, abs(r.info.obj_val))
+    tmpl.cleanup()

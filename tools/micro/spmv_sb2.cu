@@ -270,7 +270,7 @@ static void emit_block(SbHost& H, std::vector<Ent> v, int csplit, int SMAX, std:
   const int sel = cmin >= csplit;
   const int col0 = sel ? csplit + ((cmin - csplit) & ~1) : (cmin & ~1);
   const int len = (cmax - col0 + 1 + 1) & ~1;
-  if ((long long)len > 4 * (long long)v.size()) { direct.insert(direct.end(), v.begin(), v.end()); return; }
+  if ((long long)len > 16 * (long long)v.size()) { direct.insert(direct.end(), v.begin(), v.end()); return; }
   if (emit_step(H, v.data(), v.data() + v.size(), true, col0, len, sel, SMAX)) return;
   const int mid = (cmin + cmax + 1) / 2;
   std::vector<Ent> lo, hi;
@@ -414,15 +414,25 @@ void run_matrix(const char* name, const Csr& M, int csplit, const std::vector<T>
   std::vector<double> yref(R);
   for (int r = 0; r < R; r++) { double a = 0; for (int k = M.rp[r]; k < M.rp[r + 1]; k++) a += M.va[k] * src[M.ci[k]]; yref[r] = a; }
   const long long target = (long long)nnz / 148;
-  const Cfg cfgs[] = {{8192, 4096, 40960, 2, 1.0}, {8192, 3072, 45056, 2, 1.0}, {6144, 4096, 49152, 2, 1.0}, {4096, 6144, 40960, 2, 1.0},
-                      {6144, 3072, 32768, 3, 1.0}, {4096, 4096, 28672, 3, 1.0}, {8192, 2048, 24576, 3, 1.0}, {12288, 2048, 40960, 2, 1.0},
-                      {8192, 4096, 40960, 2, 0.5}, {6144, 3072, 32768, 3, 0.5}};
+  const Cfg cfgs[] = {{8192, 4096, 40960, 2, 1.0}, {8192, 2048, 20480, 4, 1.0}, {8192, 1536, 12288, 6, 1.0}, {8192, 3072, 24576, 3, 1.0},
+                      {6144, 2048, 24576, 4, 1.0}, {8192, 1024, 16384, 6, 1.0}, {10240, 2048, 16384, 4, 1.0}, {8192, 4096, 40960, 2, 0.5},
+                      {8192, 2048, 20480, 4, 0.5}, {6144, 3072, 32768, 3, 1.0}};
   if (g_cpu_only) {
-    for (const Cfg& c : {cfgs[0], cfgs[4], cfgs[7]}) {
+    for (const Cfg& c : {cfgs[0], cfgs[1], cfgs[2]}) {
       SbHost H = sb_build(M.rp, M.ci, M.va, M.ncols, csplit, c.Rmax, c.W, c.SMAX, target);
       printf("%s cpu emulation Rmax %d W %d SMAX %d: %zu panels %zu steps %lld slabs %zu combs, staged %lld direct %lld nseg %lld slices %.1f MB blobs %.1f MB, relerr %.2e\n",
              name, c.Rmax, c.W, c.SMAX, H.panels.size(), H.steps.size(), H.nslab, H.combs.size(), H.staged_entries, H.direct_entries, H.nseg,
              H.slice_elems * 8e-6, H.blobs.size() * 1e-6, sb_emulate(H, src, yref, c.W, c.SMAX, c.Rmax));
+      { // per-panel statistics
+        int worst = 0; long long worst_bytes = 0; int nd = 0;
+        for (size_t i = 0; i < H.panels.size(); i++) {
+          long long by = 0; int dsteps = 0; long long dbytes = 0;
+          for (int s = H.panels[i].step0; s < H.panels[i].step1; s++) { by += H.steps[s].blob_bytes; if (H.steps[s].direct) { dsteps++; dbytes += H.steps[s].blob_bytes; } }
+          if (i < 6 || dsteps > 0 && nd++ < 6) printf("   panel %zu: rows %d..+%d steps %d blob bytes %lld direct steps %d (%lld bytes) part %d\n", i, H.panels[i].row0, H.panels[i].nrows, H.panels[i].step1 - H.panels[i].step0, by, dsteps, dbytes, H.panels[i].part_off);
+          if (by > worst_bytes) { worst_bytes = by; worst = (int)i; }
+        }
+        printf("   heaviest panel %d: %lld blob bytes, %d steps\n", worst, worst_bytes, H.panels[worst].step1 - H.panels[worst].step0);
+      }
     }
     return;
   }
@@ -452,12 +462,16 @@ void run_matrix(const char* name, const Csr& M, int csplit, const std::vector<T>
     const size_t smem = (size_t)c.NST * (c.W * sizeof(T) + c.SMAX) + (size_t)c.Rmax * sizeof(T) + 64;
     if (smem > 232448) { printf("%s cfg skipped: %zu bytes of shared memory\n", name, smem); continue; }
     if (c.NST == 2) CK(cudaFuncSetAttribute(sb_pass<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    else CK(cudaFuncSetAttribute(sb_pass<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    else if (c.NST == 3) CK(cudaFuncSetAttribute(sb_pass<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    else if (c.NST == 4) CK(cudaFuncSetAttribute(sb_pass<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    else CK(cudaFuncSetAttribute(sb_pass<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int grid = std::min(148, V.npanels), ncomb = (int)H.combs.size();
     auto f = [&] {
       cudaMemsetAsync(counter, 0, 4);
       if (c.NST == 2) sb_pass<2><<<grid, kSbBlock, smem>>>(V, s0, s1, dy, dpart, c.W, c.SMAX, c.Rmax, counter);
-      else sb_pass<3><<<grid, kSbBlock, smem>>>(V, s0, s1, dy, dpart, c.W, c.SMAX, c.Rmax, counter);
+      else if (c.NST == 3) sb_pass<3><<<grid, kSbBlock, smem>>>(V, s0, s1, dy, dpart, c.W, c.SMAX, c.Rmax, counter);
+      else if (c.NST == 4) sb_pass<4><<<grid, kSbBlock, smem>>>(V, s0, s1, dy, dpart, c.W, c.SMAX, c.Rmax, counter);
+      else sb_pass<6><<<grid, kSbBlock, smem>>>(V, s0, s1, dy, dpart, c.W, c.SMAX, c.Rmax, counter);
       if (ncomb) sb_combine<<<dim3(8, std::min(ncomb, 64)), 256>>>(dcomb, ncomb, dpart, dy);
     };
     float a = timeit(f, 20, false), b = timeit(f, 20, true);
