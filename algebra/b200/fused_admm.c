@@ -5,7 +5,7 @@
  * compute_rhs (src/auxil.c:136-158) and 16 on update_x / update_z / update_y (auxil.c:172-229)
  * where two suffice.  auxil.c stays BYTE-IDENTICAL: the Makefile compiles it with
  *     -Dupdate_xz_tilde=osqp_ref_update_xz_tilde -Dupdate_x=osqp_ref_update_x
- *     -Dupdate_z=osqp_ref_update_z -Dupdate_y=osqp_ref_update_y
+ *     -Dupdate_z=osqp_ref_update_z -Dupdate_y=osqp_ref_update_y -Dupdate_info=osqp_ref_update_info
  * so that the reference definitions keep existing under the osqp_ref_ names (and can be selected
  * at run time with OSQP_B200_UNFUSED=1 for A/B parity runs), while the calls made by
  * src/osqp_api.c:708-726 bind to the versions below.  Expression order follows the reference's
@@ -37,6 +37,12 @@ static _Thread_local struct {
   int               checks;
 } ax_carry;
 
+static int no_ax_carry(void) {
+  static int v = -1;
+  if (v < 0) v = getenv("B200_NO_AX_CARRY") ? 1 : 0;
+  return v;
+}
+
 static int unfused(void) {
   static int v = -1;
   if (v < 0) v = getenv("OSQP_B200_UNFUSED") ? 1 : 0;
@@ -55,6 +61,7 @@ void update_xz_tilde(OSQPSolver* solver, OSQPInt admm_iter) {
   if (admm_iter == 1 || ax_carry.solver != solver) {   /* new solve: x, A, scaling may all have changed */
     ax_carry.solver = solver;
     ax_carry.valid  = 0;
+    ax_carry.checks = 0;
   }
   b200_admm_compute_rhs(work->xtilde_view->d_val, work->ztilde_view->d_val, work->x_prev->d_val,
                         work->data->q->d_val, work->z_prev->d_val, work->y->d_val,
@@ -75,6 +82,7 @@ void update_x(OSQPSolver* solver) {
     osqp_ref_update_x(solver);
     return;
   }
+  b200_range_push("admm update");      /* OSQP_PROFILER_SEC_ADMM_UPDATE */
   b200_admm_update_xzy_carry(work->x->d_val, work->delta_x->d_val, work->z->d_val, work->y->d_val,
                              work->delta_y->d_val, work->xtilde_view->d_val, work->ztilde_view->d_val,
                              work->x_prev->d_val, work->z_prev->d_val, work->data->l->d_val,
@@ -83,6 +91,7 @@ void update_x(OSQPSolver* solver) {
                              settings->alpha, (int)work->data->n, (int)work->data->m,
                              (ax_carry.valid && ax_carry.solver == solver && work->data->m > 0)
                                  ? work->Ax->d_val : OSQP_NULL);
+  b200_range_pop();
 }
 
 void update_z(OSQPSolver* solver) {
@@ -111,14 +120,15 @@ void update_info(OSQPSolver* solver, OSQPInt iter, OSQPInt polishing) {
     return;
   }
   info->iter = iter;
+  b200_range_push("termination check");
 
   if (m) {
     /* A x: carried by the fused x/z/y update since the last exact product of this solve */
     if (!(ax_carry.valid && ax_carry.solver == solver) || ++ax_carry.checks >= AX_EXACT_EVERY ||
-        getenv("B200_NO_AX_CARRY")) {
+        no_ax_carry()) {
       OSQPMatrix_Axpy(work->data->A, work->x, work->Ax, 1.0, 0.0);
       ax_carry.checks = 0;
-      ax_carry.valid  = (ax_carry.solver == solver) && !getenv("B200_NO_AX_CARRY");
+      ax_carry.valid  = (ax_carry.solver == solver) && !no_ax_carry();
     }
   }
   OSQPMatrix_Axpy(work->data->P, work->x, work->Px, 1.0, 0.0);
@@ -129,6 +139,7 @@ void update_info(OSQPSolver* solver, OSQPInt iter, OSQPInt polishing) {
                       work->data->u->d_val, settings->scaling ? work->scaling->Einv->d_val : OSQP_NULL,
                       settings->scaling ? work->scaling->Dinv->d_val : OSQP_NULL,
                       OSQP_INFTY * OSQP_MIN_SCALING, OSQP_ZERO_DEADZONE, (int)n, (int)m, r);
+  b200_range_pop();
 
   /* primal residual (compute_prim_res) */
   if (m == 0) {

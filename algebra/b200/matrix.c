@@ -482,8 +482,25 @@ void OSQPMatrix_row_norm_inf(const OSQPMatrix* M, OSQPVectorf* E) {
 }
 
 /* ------------------------------------------------------------ row extraction
- * keeps row j iff rows[j] != 0, order preserved (csc_utils.c:134-203); used by polish only,
- * so it goes through the host. */
+ * keeps row j iff rows[j] != 0, order preserved (csc_utils.c:134-203); used by polish
+ * (src/polish.c:317-372).  On the device: the kept rows of CSR(A) are compacted (flag scan + one warp
+ * per row) and CSR(A_red') is the device transpose of the result; nothing is downloaded.  The host
+ * filter below remains for the corner cases the device path declines (nothing kept, empty matrix,
+ * a column of A_red longer than the rank-sort limit) and for B200_HOST_TRANSPOSE=1. */
+static OSQPMatrix* submatrix_byrows_device(const OSQPMatrix* A, const OSQPVectori* rows) {
+  int         mred = 0;
+  OSQPMatrix* out;
+  b200_csr*   S = b200_csr_select_rows(A->S, rows->d_val, &mred);
+  if (!S) return OSQP_NULL;
+  out = (OSQPMatrix*)c_calloc(1, sizeof(OSQPMatrix));
+  if (!out) { b200_csr_destroy(S); return OSQP_NULL; }
+  out->S  = S;
+  out->St = b200_csr_transpose(S, OSQP_NULL);
+  if (!out->St) { OSQPMatrix_free(out); return OSQP_NULL; }
+  out->m = mred; out->n = A->n; out->nnz_user = b200_csr_nnz(S); out->is_symmetric = 0;
+  return out;
+}
+
 OSQPMatrix* OSQPMatrix_submatrix_byrows(const OSQPMatrix* A, const OSQPVectori* rows) {
   OSQPInt        m = A->m, n = A->n, nnz = A->nnz_user;
   OSQPInt        i, j, k, mred = 0, nzred = 0;
@@ -497,6 +514,10 @@ OSQPMatrix* OSQPMatrix_submatrix_byrows(const OSQPMatrix* A, const OSQPVectori* 
   if (A->is_symmetric) {
     c_eprint("row selection not implemented for partially filled matrices");
     return OSQP_NULL;
+  }
+  if (!getenv("B200_HOST_TRANSPOSE") && A->m > 0) {
+    out = submatrix_byrows_device(A, rows);
+    if (out) return out;
   }
 
   flags  = (OSQPInt*)c_malloc(((size_t)m + 1) * sizeof(OSQPInt));

@@ -39,8 +39,12 @@ static void configure(b200pcg_solver* s) {
 static OSQPInt solve_linsys_b200pcg(b200pcg_solver* s, OSQPVectorf* b, OSQPInt admm_iter) {
   double pr = s->scaled_prim_res ? (double)*s->scaled_prim_res : 0.0;
   double dr = s->scaled_dual_res ? (double)*s->scaled_dual_res : 0.0;
-  return b200_pcg_solve(s->pcg, b->d_val, (int)admm_iter, pr, dr, (int)s->max_iter,
-                        (double)s->tol_fraction, (int)s->reduction_threshold);
+  OSQPInt rc;
+  b200_range_push("linsys solve");     /* OSQP_PROFILER_SEC_LINSYS_SOLVE */
+  rc = b200_pcg_solve(s->pcg, b->d_val, (int)admm_iter, pr, dr, (int)s->max_iter,
+                      (double)s->tol_fraction, (int)s->reduction_threshold);
+  b200_range_pop();
+  return rc;
 }
 
 static void update_settings_b200pcg(b200pcg_solver* s, const OSQPSettings* settings) {
@@ -127,12 +131,14 @@ OSQPInt init_linsys_solver_b200pcg(b200pcg_solver** sp, const OSQPMatrix* P, con
   s->update_settings    = &update_settings_b200pcg;
 
   double t0 = now_ms();
+  b200_range_push("linsys init");      /* OSQP_PROFILER_SEC_LINSYS_INIT */
   s->pcg = b200_pcg_create(P->S, A->S, A->St, (int)s->n, (int)s->m);
-  if (!s->pcg) return OSQP_MEM_ALLOC_ERROR;
+  if (!s->pcg) { b200_range_pop(); return OSQP_MEM_ALLOC_ERROR; }
 
   configure(s);
   b200_pcg_refresh_matrices(s->pcg);
   b200_pcg_refresh_precond(s->pcg);
+  b200_range_pop();
   if (getenv("B200_TRACE_SETUP")) { b200_sync(); fprintf(stderr, "[b200 trace] linsys init %.1f ms\n", now_ms() - t0); }
   return 0;
 }

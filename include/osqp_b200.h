@@ -53,6 +53,10 @@ unsigned long long b200_graph_launch_count(void);
 /* launch tracer (development aid): with B200_TRACE_FILE set, every launch / collective records a
  * CUDA event + host time, dumped as CSV at b200_shutdown; this adds a named marker */
 void b200_trace_mark(const char* tag);
+/* NVTX ranges named after the reference's profiler sections (include/private/profilers.h:16-31:
+ * "linsys init", "linsys solve", "admm update", "termination check"); active with B200_NVTX=1 */
+void b200_range_push(const char* name);
+void b200_range_pop(void);
 /* CUDA-event timing on the library stream (bench.py / profiling only) */
 void* b200_event_create(void);
 void  b200_event_destroy(void* ev);
@@ -141,6 +145,11 @@ void b200_csr_destroy(b200_csr* M);
  * replaces csr_transpose (algebra/cuda/src/cuda_csr.cu:489-560: thrust sort + cusparseCsr2cscEx2) */
 b200_csr* b200_csr_transpose(const b200_csr* Mt, int** d_map_out);
 void b200_veci_gather(int* d_dst, const int* d_src, const int* d_idx, int n);
+/* The rows of M with d_flags[row] != 0 (order preserved) as a new matrix, built on the device (flag scan,
+ * row-length scan, one warp per kept row).  NULL when nothing is kept or on failure (caller keeps its
+ * host path).  replaces csr_submatrix_byrows (algebra/cuda/src/cuda_csr.cu:763-843) for
+ * OSQPMatrix_submatrix_byrows (polish, src/polish.c:317-372) */
+b200_csr* b200_csr_select_rows(const b200_csr* M, const int* d_flags, int* nrows_out);
 /* Full symmetric CSR (structurally full diagonal: lower mirrors ++ zero diagonal if missing ++ upper
  * triangle, per row) from the upper-triangular CSC arrays of P (host pointers), expanded on the
  * device.  *d_map_u / *d_map_l: device arrays of nnz ints, position of every user entry itself and

@@ -10,6 +10,7 @@
 #include <vector>
 #include <atomic>
 #include <thread>
+#include <nvtx3/nvToolsExt.h>   // header-only: resolves the tools injection library at first use, a no-op otherwise
 
 namespace b200 {
 Context& ctx() {
@@ -264,6 +265,20 @@ unsigned long long b200_graph_launch_count(void) { return ctx().graph_launches; 
 
 void b200_trace_mark(const char* tag) {
   if (ctx().trace_on) trace_point(strdup(tag ? tag : "mark"));   // tags live until the dump
+}
+
+// NVTX ranges (Nsight Systems / Compute timelines): the sections the reference annotates through
+// osqp_profiler_sec_push / pop (include/private/profilers.h:16-31; OSQP_PROFILER_SEC_LINSYS_SOLVE around
+// cuda_pcg.cu:159-161).  Active with B200_NVTX=1 so that the unprofiled path pays one branch.
+static bool nvtx_on() {
+  static const bool on = getenv("B200_NVTX") != nullptr;
+  return on;
+}
+void b200_range_push(const char* name) {
+  if (nvtx_on()) nvtxRangePushA(name ? name : "b200");
+}
+void b200_range_pop(void) {
+  if (nvtx_on()) nvtxRangePop();
 }
 
 void* b200_event_create(void) {

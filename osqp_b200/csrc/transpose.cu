@@ -254,6 +254,33 @@ __global__ void __launch_bounds__(kBlock) sym_map_u(int nnz, const int* __restri
 
 namespace {
 
+// ---- row selection (OSQPMatrix_submatrix_byrows): flags -> 0/1, lengths of the kept rows, row copy
+__global__ void __launch_bounds__(kBlock) sel_mark(int n, const int* __restrict__ flags, int* sel) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) sel[i] = flags[i] != 0;
+}
+// pos[i] = inclusive scan of sel: a kept row i becomes row pos[i] - 1; lens[new + 1] = its length
+__global__ void __launch_bounds__(kBlock) sel_lens(int n, const int* __restrict__ flags, const int* __restrict__ pos,
+                                                   const int* __restrict__ rp, int* lens) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+    if (flags[i] != 0) lens[pos[i]] = rp[i + 1] - rp[i];
+}
+// one warp per source row
+__global__ void __launch_bounds__(kBlock) sel_copy(int n, const int* __restrict__ flags, const int* __restrict__ pos,
+                                                   const int* __restrict__ rp, const int* __restrict__ ci,
+                                                   const T* __restrict__ v, const int* __restrict__ rp_red, int* ci_red,
+                                                   T* v_red) {
+  const int lane = threadIdx.x & 31, wpb = kBlock >> 5;
+  for (int i = blockIdx.x * wpb + (threadIdx.x >> 5); i < n; i += gridDim.x * wpb) {
+    if (flags[i] == 0) continue;
+    const int s0 = rp[i], e0 = rp[i + 1], d0 = rp_red[pos[i] - 1];
+    for (int k = s0 + lane; k < e0; k += 32) { ci_red[d0 + k - s0] = ci[k]; v_red[d0 + k - s0] = v[k]; }
+  }
+}
+
+}  // namespace
+
+namespace {
+
 // prefix sum over data[0..n) in place (inclusive); optionally the largest input value
 bool device_scan(int* d_data, int n, int* d_max, cudaStream_t st) {
   const int nchunks = (n + kScanChunk - 1) / kScanChunk;
@@ -348,6 +375,66 @@ b200_csr* b200_csr_transpose(const b200_csr* Mt, int** d_map_out) {
   if (d_map_out) *d_map_out = nullptr;
   if (!Mt) return nullptr;
   return transpose_impl(Mt->d_row_ptr, Mt->d_col_ind, Mt->d_val, Mt->nrows, Mt->ncols, Mt->nnz, true, d_map_out);
+}
+
+// The rows of M whose flag is non-zero, order preserved, as a new CSR with its row-block schedule -- on the
+// device: flag scan, row-length scan, one warp per kept row (replaces the host filter of round 1; the
+// reference's role: csr_submatrix_byrows, algebra/cuda/src/cuda_csr.cu:763-843).  NULL on failure or when
+// nothing is kept (the caller keeps its host path).
+b200_csr* b200_csr_select_rows(const b200_csr* M, const int* d_flags, int* nrows_out) {
+  Context& c = ctx();
+  cudaStream_t st = c.stream;
+  if (nrows_out) *nrows_out = 0;
+  if (!M || M->nrows <= 0 || M->nnz <= 0) return nullptr;
+  const int n = M->nrows, cap = c.sm_count * 8;
+  int* d_pos = nullptr;
+  int h_kept = 0, h_nnz = 0;
+  bool ok = B200_CHECK(dev_malloc(&d_pos, sizeof(int) * ((size_t)n + 1)));
+  b200_csr* R = nullptr;
+  int* d_rp = nullptr;
+  if (ok) {
+    int g = (n + kBlock - 1) / kBlock;
+    sel_mark<<<g < cap ? g : cap, kBlock, 0, st>>>(n, d_flags, d_pos);
+    count_launch();
+    ok &= device_scan(d_pos, n, nullptr, st);
+    ok &= B200_CHECK(cudaMemcpyAsync(&h_kept, d_pos + n - 1, sizeof(int), cudaMemcpyDeviceToHost, st));
+    ok &= B200_CHECK(cudaStreamSynchronize(st));
+  }
+  if (ok && h_kept > 0) {
+    ok &= B200_CHECK(dev_malloc(&d_rp, sizeof(int) * ((size_t)h_kept + 2 * kPad)));
+    if (ok) {
+      ok &= B200_CHECK(cudaMemsetAsync(d_rp, 0, sizeof(int) * ((size_t)h_kept + 1), st));
+      int g = (n + kBlock - 1) / kBlock;
+      sel_lens<<<g < cap ? g : cap, kBlock, 0, st>>>(n, d_flags, d_pos, M->d_row_ptr, d_rp);
+      count_launch();
+      ok &= device_scan(d_rp, h_kept + 1, nullptr, st);
+      ok &= B200_CHECK(cudaMemcpyAsync(&h_nnz, d_rp + h_kept, sizeof(int), cudaMemcpyDeviceToHost, st));
+      ok &= B200_CHECK(cudaStreamSynchronize(st));
+    }
+    if (ok && h_nnz > 0) {
+      R = new b200_csr();
+      R->nrows = h_kept; R->ncols = M->ncols; R->nnz = h_nnz;
+      R->d_row_ptr = d_rp; d_rp = nullptr;
+      ok &= B200_CHECK(dev_malloc(&R->d_col_ind, sizeof(int) * ((size_t)h_nnz + 2 * kPad)));
+      ok &= B200_CHECK(dev_malloc(&R->d_val, sizeof(T) * ((size_t)h_nnz + 2 * kPad)));
+      if (ok) {
+        const int wpb = kBlock >> 5;
+        int g = (n + wpb - 1) / wpb;
+        sel_copy<<<g < cap ? g : cap, kBlock, 0, st>>>(n, d_flags, d_pos, M->d_row_ptr, M->d_col_ind, M->d_val,
+                                                        R->d_row_ptr, R->d_col_ind, R->d_val);
+        count_launch();
+        std::vector<int> h_rp((size_t)h_kept + 1);
+        ok &= B200_CHECK(cudaMemcpyAsync(h_rp.data(), R->d_row_ptr, sizeof(int) * ((size_t)h_kept + 1), cudaMemcpyDeviceToHost, st));
+        ok &= B200_CHECK(cudaStreamSynchronize(st));
+        if (ok) ok = b200_build_schedule(R, h_rp.data()) == 0;
+      }
+      if (!ok) { b200_csr_destroy(R); R = nullptr; }
+    }
+  }
+  dev_free(d_pos);
+  dev_free(d_rp);
+  if (R && nrows_out) *nrows_out = h_kept;
+  return R;
 }
 
 // Full symmetric CSR with a structurally full diagonal from the upper-triangular CSC arrays of P

