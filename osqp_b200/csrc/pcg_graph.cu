@@ -562,9 +562,10 @@ __global__ void g_step_scalars(PcgRun* run) {
 }
 
 // ---------------------------------------------------------------------------------------------
-// Lean passes (matrices without over-long rows): the same CSR-stream tile as spmv_pass, written
-// out flat -- 512 threads per 2048-entry tile, a single batch of 4 (col, val, gather) chains per
-// thread, no long-row branch, no generic functors (<= 42 registers, 3 CTAs per SM).  The grid is
+// Lean passes: the same CSR-stream tile as spmv_pass, written out flat -- 512 threads per 2048-entry
+// tile, a single batch of 4 (col, val, gather) chains per thread, no generic functors (<= 42
+// registers, 3 CTAs per SM); chunks of rows longer than a tile are summed CTA-wide and folded by the
+// last chunk to arrive.  The grid is
 // ONE WAVE (3 CTAs per SM) looping over the tiles round-robin: the per-CTA tail -- block
 // reduction of the dot-product partials, publication, ticket -- is then paid 444 times per pass
 // instead of once per tile (6100 times for the Lasso operator), which measured 45 us of a 120 us
@@ -602,10 +603,44 @@ __global__ void __launch_bounds__(kLeanBlock, kLeanCtasPerSm) g_lean_pass(int sl
   const int n = a.n;
   const int tid = threadIdx.x;
   double acc = 0.0, acc1 = 0.0, acc2 = 0.0;
+  // what happens to a finished row sum (exactly once per row, by one thread)
+  auto emit = [&](int row, T sum) {
+    if (MODE == 0) {
+      a.w[row] = sum;
+      a.t[row] = (a.rho_vec ? a.rho_vec[row] : a.rho) * sum;
+    } else if (MODE == 3) {
+      a.Ax[row] = sum;
+      a.t[row]  = (a.rho_vec ? a.rho_vec[row] : a.rho) * (sum - a.b[n + row]);
+    } else if (MODE == 7) {
+      a.Kp[row] = sum;
+      if (row >= n_shared) {
+        const T yk = a.minv[row] * sum;
+        acc  += (double)src[row] * (double)sum;
+        acc1 += (double)a.r[row] * (double)yk;
+        acc2 += (double)sum * (double)yk;
+      }
+    } else if (MODE >= 4) {
+      a.Kp[row] = sum;
+    } else if (MODE == 1) {
+      // Kp and the three dots that fix alpha AND beta before the vector update:
+      //   r+ = r + alpha Kp  =>  r+' M^-1 r+ = r'y + 2 alpha r'M^-1 Kp + alpha^2 Kp'M^-1 Kp
+      a.Kp[row] = sum;
+      const T yk = a.minv[row] * sum;
+      acc  += (double)src[row] * (double)sum;
+      acc1 += (double)a.r[row] * (double)yk;
+      acc2 += (double)sum * (double)yk;
+    } else {
+      const T rr = sum - a.b[row];
+      const T yy = a.minv[row] * rr;
+      a.r[row] = rr;
+      a.p[row] = -yy;
+      acc  += (double)rr * (double)yy;
+      acc1 = fmax(acc1, fabs((double)rr));
+    }
+  };
   for (int b = blockIdx.x; b < nblocks; b += gridDim.x) {
     const int4 d = __ldg(desc + b);
-    const int nnz0 = d.z, cnt = d.w, nrows = d.y & 0xffffff, lg = d.y >> 24;
-    for (int i = tid; i <= nrows; i += kLeanBlock) srp[i] = ld_stream(row_ptr + d.x + i) - nnz0;
+    const int nnz0 = d.z, cnt = d.w;
     int c[4];
     T   v[4];
 #pragma unroll
@@ -616,6 +651,41 @@ __global__ void __launch_bounds__(kLeanBlock, kLeanCtasPerSm) g_lean_pass(int sl
         v[u] = ld_stream(val + nnz0 + k);
       }
     }
+    if (d.y < 0) {
+      // ---- one <= kTile-entry chunk of a row longer than a tile (e.g. the 1e4-entry feature rows of A' in
+      // BASELINE configs[3]): CTA-wide sum, partial published, the LAST chunk to arrive folds the partials in
+      // chunk order (integer ticket: deterministic, no floating-point atomics) and emits the row
+      const int  lr   = -d.y - 1;
+      const int4 info = __ldg(M.long_rows + lr);       // {row, first block, chunks, -}
+      double part = 0.0;
+#pragma unroll
+      for (int u = 0; u < 4; u++) {
+        const int k = u * kLeanBlock + tid;
+        if (k < cnt) part += (double)(kOverA ? v[u] * src[c[u]] : v[u] * (c[u] < n ? src[c[u]] : t[c[u] - n]));
+      }
+      part = block_sum(part, shr);
+      __shared__ int s_lastchunk;
+      if (tid == 0) {
+        M.long_partials[b] = part;
+        __threadfence();
+        s_lastchunk = (atomicAdd(&M.long_counters[lr], 1u) == (unsigned)(info.z - 1));
+      }
+      __syncthreads();
+      if (s_lastchunk) {
+        __threadfence();
+        double tot = 0.0;
+        for (int k = tid; k < info.z; k += kLeanBlock) tot += __ldcg(&M.long_partials[info.y + k]);
+        tot = block_sum(tot, shr);
+        if (tid == 0) {
+          M.long_counters[lr] = 0;
+          emit(info.x, (T)tot);
+        }
+      }
+      __syncthreads();
+      continue;
+    }
+    const int nrows = d.y & 0xffffff, lg = d.y >> 24;
+    for (int i = tid; i <= nrows; i += kLeanBlock) srp[i] = ld_stream(row_ptr + d.x + i) - nnz0;
 #pragma unroll
     for (int u = 0; u < 4; u++) {
       const int k = u * kLeanBlock + tid;
@@ -634,41 +704,7 @@ __global__ void __launch_bounds__(kLeanBlock, kLeanCtasPerSm) g_lean_pass(int sl
         for (int k = srp[r] + lig; k < e; k += g) sum += sm[k];
       }
       for (int o = g >> 1; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
-      if (r < nrows && lig == 0) {
-        const int row = d.x + r;
-        if (MODE == 0) {
-          a.w[row] = sum;
-          a.t[row] = (a.rho_vec ? a.rho_vec[row] : a.rho) * sum;
-        } else if (MODE == 3) {
-          a.Ax[row] = sum;
-          a.t[row]  = (a.rho_vec ? a.rho_vec[row] : a.rho) * (sum - a.b[n + row]);
-        } else if (MODE == 7) {
-          a.Kp[row] = sum;
-          if (row >= n_shared) {
-            const T yk = a.minv[row] * sum;
-            acc  += (double)src[row] * (double)sum;
-            acc1 += (double)a.r[row] * (double)yk;
-            acc2 += (double)sum * (double)yk;
-          }
-        } else if (MODE >= 4) {
-          a.Kp[row] = sum;
-        } else if (MODE == 1) {
-          // Kp and the three dots that fix alpha AND beta before the vector update:
-          //   r+ = r + alpha Kp  =>  r+' M^-1 r+ = r'y + 2 alpha r'M^-1 Kp + alpha^2 Kp'M^-1 Kp
-          a.Kp[row] = sum;
-          const T yk = a.minv[row] * sum;
-          acc  += (double)src[row] * (double)sum;
-          acc1 += (double)a.r[row] * (double)yk;
-          acc2 += (double)sum * (double)yk;
-        } else {
-          const T rr = sum - a.b[row];
-          const T yy = a.minv[row] * rr;
-          a.r[row] = rr;
-          a.p[row] = -yy;
-          acc  += (double)rr * (double)yy;
-          acc1 = fmax(acc1, fabs((double)rr));
-        }
-      }
+      if (r < nrows && lig == 0) emit(d.x + r, sum);
     }
     __syncthreads();   // sm / srp are reused by the next tile
   }
@@ -714,12 +750,15 @@ inline int lean_grid(const b200_csr& M, bool reduces = true) {
   return g > 0 ? g : 1;
 }
 
-// the flat kernel does not handle chunks of over-long rows
+// the flat kernel takes every tile the schedule builder produces (normal blocks of <= kTile entries and
+// <= kTile-entry chunks of over-long rows); B200_PCG_LEAN_NO_LONG=1 restores the round-1 restriction
 static bool lean_ok(const b200_csr& M, const std::vector<int4>& desc) {
-  if (M.nlong > 0) return false;
-  for (const int4& d : desc)
-    if (d.y < 0) return false;
-  return true;
+  static const bool no_long = getenv("B200_PCG_LEAN_NO_LONG") != nullptr;
+  for (const int4& d : desc) {
+    if (d.w > kTile) return false;
+    if (d.y < 0 && no_long) return false;
+  }
+  return !(no_long && M.nlong > 0);
 }
 
 // first node of the loop graph: arm the WHILE condition from the initial residual
@@ -1091,6 +1130,25 @@ int b200_pcg_sharded_solve(b200_pcg* s, const PcgArgs& a) {
     g_rhs_norm_sum<<<gn, kBlock, 0, st>>>(d_args, run, s->d_gred, cap, 1, off);
     count_launch("g_rhs_norm_sum");
     exchange_scalars(&run->rhs_norm, 1, true);
+  }
+  if (s->p2p) {
+    // peer-memory path: no NCCL call and no host read-back from here on; the loop is the graph
+    if (a.ax_valid) g_p1_carried<<<ew_grid(m), kBlock, 0, st>>>(d_args);
+    else g_lean_pass<3><<<lean_grid(*s->A, false), kLeanBlock, 0, st>>>(d_args, run, s->d_gred, cap);
+    count_launch("P1");
+    g_lean_pass<6><<<lean_grid(s->K2, false), kLeanBlock, 0, st>>>(d_args, run, s->d_gred, cap);
+    count_launch("P2 partial");
+    g_xchg_vector<0><<<xchg_grid(dist_n_shared()), kBlock, 0, st>>>(d_args, run, s->d_gred, cap);
+    count_launch("xchg(vector)");
+    g_resid_init<<<gn, kBlock, 0, st>>>(d_args, run, s->d_gred, cap, off, 1);
+    count_launch("g_resid_init+xchg(scalars)");
+    const bool okg = B200_CHECK(cudaGraphLaunch((cudaGraphExec_t)s->graph_exec, st));
+    count_launch("graph(loop)");
+    ctx().graph_launches++;
+    const int nm1 = n > m ? n : m;
+    g_epilogue<<<ew_grid(nm1), kBlock, 0, st>>>(d_args, run);
+    count_launch("g_epilogue");
+    return okg ? 0 : 1;
   }
   g_tolerance<<<1, 32, 0, st>>>(d_args, run);
   count_launch("g_tolerance");

@@ -44,11 +44,14 @@ def test_two_rank_sharded_solve_matches_oracle(family, layout, exchange):
     res, out = _run_worker(["--family", family, "--scale", "0.003", "--check", "--layout", layout],
                            {"B200_DIST_NO_P2P": "1"} if exchange == "nccl" else None)
     assert res["PARITY"] == "OK", res
-    if exchange == "p2p" and family != "portfolio":          # portfolio: the dense budget row is an over-long row
-        assert res["p2p"] is True
-        assert res["allreduce_calls"] < res["cg_iters"], res    # no collective inside the CG loop
+    # the NCCL path needs 3 collectives per CG iteration and 2 per linear solve for its CG loops alone;
+    # what both paths share are the ~6 collectives of a termination check and the setup-time norms
+    cg_loop_calls = 3 * res["cg_iters"] + 2 * res["solves"]
+    if exchange == "p2p":
+        assert res["p2p"] is True and res["graph_launches"] >= res["solves"], res   # the loop ran as a CUDA graph
+        assert res["allreduce_calls"] < cg_loop_calls, res       # no collective inside the CG loop
     else:
-        assert res["allreduce_calls"] > res["cg_iters"]          # one exchange per K.p (+ residual checks)
+        assert res["allreduce_calls"] > cg_loop_calls and res["graph_launches"] == 0, res
     if layout == "split" and family != "portfolio":         # epigraph families: only the features are shared
         assert res["n_shared"] < 0.2 * res["n"], res
     assert "REPLICATED_X_IDENTICAL True" in out.stdout
@@ -61,5 +64,6 @@ def test_two_rank_block_seeded_shards_match_oracle(family):
     ShardedOSQP.setup_local; the assembled solution matches the oracle on the assembled global QP."""
     res, out = _run_worker(["--family", family, "--scale", "0.003", "--check", "--blocks"])
     assert res["PARITY"] == "OK" and res["blocks"] is True, res
-    assert res["p2p"] is True and res["allreduce_calls"] < res["cg_iters"], res
+    assert res["p2p"] is True and res["graph_launches"] >= res["solves"], res
+    assert res["allreduce_calls"] < 3 * res["cg_iters"] + 2 * res["solves"], res
     assert "REPLICATED_X_IDENTICAL True" in out.stdout

@@ -45,6 +45,17 @@ def test_golden_solutions(b200_lib, case, kw, polishing):
     assert close(r.info.obj_val, d["obj_value_test"])
 
 
+@pytest.mark.parametrize("driver", ["persistent", "graph"])
+def test_large_qp(b200_lib, monkeypatch, driver):
+    """tests/large_qp/test_large_qp.cpp:10-44 with the indirect solver: status and objective 0.106081 to
+    TESTS_TOL relative"""
+    monkeypatch.setenv("B200_PCG_DRIVER", driver)
+    d = load_golden("large_qp")
+    s, r = run(b200_lib, d)
+    assert r.info.status_val == _capi.OSQP_SOLVED
+    assert abs(r.info.obj_val - d["obj_value_test"]) / abs(d["obj_value_test"]) < TESTS_TOL
+
+
 def test_basic_qp2_update_vectors(b200_lib):
     d = load_golden("basic_qp2")
     s, r = run(b200_lib, d, eps_abs=1e-6, eps_rel=1e-6, warm_starting=1, polishing=1)

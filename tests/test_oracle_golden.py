@@ -44,6 +44,15 @@ def test_reference_golden_solutions(oracle_lib, case, kw, polishing):
     assert close(r.info.obj_val, d["obj_value_test"]) * max(1.0, abs(d["obj_value_test"]))
 
 
+def test_large_qp(oracle_lib):
+    """tests/large_qp/test_large_qp.cpp:10-44 (n = 160, m = 270): status and objective 0.106081 to TESTS_TOL
+    relative"""
+    d = load_golden("large_qp")
+    s, r = solve(oracle_lib, d)
+    assert r.info.status_val == _capi.OSQP_SOLVED
+    assert abs(r.info.obj_val - d["obj_value_test"]) / abs(d["obj_value_test"]) < TESTS_TOL
+
+
 def test_basic_qp2_update(oracle_lib):
     d = load_golden("basic_qp2")
     s, r = solve(oracle_lib, d, eps_abs=1e-6, eps_rel=1e-6, warm_starting=1, polishing=1)

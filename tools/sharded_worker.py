@@ -83,10 +83,11 @@ else:
     x, y = prob.gather(r, dist)
     n_shared_out = int(prob.plan["shared"].size) if prob.plan is not None else n
 k.b200_dist_p2p_enabled.restype = __import__("ctypes").c_int
+k.b200_graph_launch_count.restype = __import__("ctypes").c_ulonglong
 ncalls = __import__("ctypes").c_ulonglong(0); nbytes = __import__("ctypes").c_ulonglong(0)
 k.b200_dist_stats(__import__("ctypes").byref(ncalls), __import__("ctypes").byref(nbytes))
 if rank == 0:
-    out = dict(family=args.family, n=n, m=m, nnzA=int(pb["A"].nnz), world=world, p2p=bool(k.b200_dist_p2p_enabled()),
+    out = dict(family=args.family, n=n, m=m, nnzA=int(pb["A"].nnz), world=world, p2p=bool(k.b200_dist_p2p_enabled()), graph_launches=int(k.b200_graph_launch_count()),
                blocks=bool(args.blocks), status=r.info.status, iters=r.info.iter,
                obj=r.info.obj_val, prim_res=r.info.prim_res, dual_res=r.info.dual_res, cg_iters=cg, solves=ns,
                setup_s=t1 - t0, solve_s=best, iters_per_s=r.info.iter / best, allreduce_calls=ncalls.value,
