@@ -715,6 +715,8 @@ def run_sharded(args):
     if k.b200_graph_launch_count() - g0 > 0:
         launches += (4 if p2p else 3) * (cg1 - cg0)
     status, obj = r.info.status, r.info.obj_val
+    if world > 1 and k.b200_dist_p2p_error() != 0:
+        raise RuntimeError("peer-memory exchange timed out: a rank never arrived")
     phases = pcg_phases(k) if prec == "f64" else None     # this rank's passes, timed alone (no exchange)
     solver.cleanup()
 

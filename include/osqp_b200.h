@@ -326,6 +326,7 @@ void b200_dist_stats(unsigned long long* n_calls, unsigned long long* bytes);
 int  b200_dist_p2p_export(unsigned char* handle64);
 int  b200_dist_p2p_import(const unsigned char* handles, int world);   /* world x 64 bytes */
 int  b200_dist_p2p_enabled(void);
+int  b200_dist_p2p_error(void);     /* 1: an exchange timed out (a peer never arrived); synchronises */
 
 /* bumped by every kernel launch / device copy of the library: lets the backend cache scalars and
  * know when they went stale */

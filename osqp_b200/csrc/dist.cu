@@ -220,6 +220,18 @@ int b200_dist_p2p_import(const unsigned char* handles, int world) {
 
 int b200_dist_p2p_enabled(void) { return dist_p2p_ready() ? 1 : 0; }
 
+// 1 if a wait of the peer-memory exchange ever ran into its time limit (a peer never arrived): the results
+// since then are meaningless.  Synchronises the library stream.
+int b200_dist_p2p_error(void) {
+  if (!p2p.mine) return 0;
+  XchgState h;
+  memset(&h, 0, sizeof(h));
+  cudaStreamSynchronize(ctx().stream);
+  if (cudaMemcpy(&h, p2p.mine + kXchgTotalDoubles, sizeof(h), cudaMemcpyDeviceToHost) != cudaSuccess) return 2;
+  if (h.err && !ctx().last_error) ctx().last_error = 20000;
+  return h.err;
+}
+
 
 void b200_dist_stats(unsigned long long* n_calls, unsigned long long* bytes) {
   if (n_calls) *n_calls = g.n_allreduce;

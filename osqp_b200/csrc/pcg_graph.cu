@@ -121,7 +121,7 @@ __constant__ PcgArgs c_args[kMaxContexts];   // one block per library context (h
 
 // ---- peer-memory exchange (row-sharded solve; buffers and protocol: common.cuh / dist.cu) -------------
 __constant__ XchgView c_xchg;
-constexpr unsigned long long kXchgTimeoutNs = 20ull * 1000ull * 1000ull * 1000ull;   // a peer that never arrives
+constexpr unsigned long long kXchgTimeoutNs = 4ull * 1000ull * 1000ull * 1000ull;   // a peer that never arrives
 
 __device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
   asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
@@ -139,6 +139,7 @@ __device__ __forceinline__ unsigned long long globaltimer_ns() {
 // spin until the sequence word reaches `seq` (written by a peer over NVLink); bounded, so that a rank
 // whose peer died reports an error instead of hanging the GPU
 __device__ __forceinline__ bool xchg_wait(const unsigned long long* flag, unsigned long long seq) {
+  if (*(volatile int*)&c_xchg.state->err) return false;     // already failed once: never wait again
   const unsigned long long t0 = globaltimer_ns();
   unsigned spins = 0;
   while (ld_acquire_sys(flag) < seq) {
