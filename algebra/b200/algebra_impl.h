@@ -15,15 +15,22 @@
 extern "C" {
 #endif
 
+/* how a vector is laid out over the ranks of a row-sharded solve (B200_SHARD_*): fixed when the vector
+ * is CREATED (constructors / views / copies in vector.c) and read by every reduction -- not re-derived
+ * from its length at each use */
+enum { B200_SHARD_NONE = 0, B200_SHARD_ROWS = 1, B200_SHARD_COLSPLIT = 2 };
+
 struct OSQPVectori_ {
   OSQPInt* d_val;     /* device array */
   OSQPInt  length;
+  OSQPInt  shard;     /* B200_SHARD_* */
 };
 
 struct OSQPVectorf_ {
   OSQPFloat* d_val;   /* device array (b200_float == OSQPFloat) */
   OSQPInt    length;
   OSQPInt    is_view; /* 1: d_val aliases a parent vector and is not freed */
+  OSQPInt    shard;   /* B200_SHARD_* */
 };
 
 /*
@@ -67,6 +74,10 @@ extern OSQPInt b200_dist_mlocal;
 extern OSQPInt b200_dist_nshared;   /* -1: layout off */
 extern OSQPInt b200_dist_nglobal;   /* global number of columns (mean over columns in scaling.c:123-124) */
 #define B200_IS_COLSPLIT(len) (b200_dist_nshared >= 0 && (len) == b200_dist_n && b200_dist_world() > 1)
+/* classification of a NEW vector of this length under the layout declared by osqp_b200_dist_configure*:
+ * the core only ever creates vectors of n (columns), m (rows) and n + m entries between osqp_setup and
+ * osqp_cleanup; polish (vectors of other lengths over subsets of the rows) is refused when sharded */
+#define B200_SHARD_OF(len) (B200_IS_SHARDED(len) ? B200_SHARD_ROWS : (B200_IS_COLSPLIT(len) ? B200_SHARD_COLSPLIT : B200_SHARD_NONE))
 
 /*
  * Scalar cache: the fused termination check (fused_admm.c) computes every norm the core asks for

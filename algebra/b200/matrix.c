@@ -434,7 +434,8 @@ void OSQPMatrix_Axpy(const OSQPMatrix* A, const OSQPVectorf* x, OSQPVectorf* y, 
 void OSQPMatrix_Atxpy(const OSQPMatrix* A, const OSQPVectorf* x, OSQPVectorf* y, OSQPFloat alpha,
                       OSQPFloat beta) {
   if (y->length <= 0) return;
-  if (!A->is_symmetric && b200_dist_world() > 1 && b200_dist_mlocal >= 0) {
+  if (!A->is_symmetric && b200_dist_world() > 1 && b200_dist_mlocal >= 0 && A->m == b200_dist_mlocal &&
+      x->shard == B200_SHARD_ROWS) {   /* the rank's row block of the constraint matrix, not e.g. a polish submatrix */
     /* row-sharded A: A'x = sum over ranks of A_r' x_r -> one all-reduce of the length-n result.
        beta y must be added once, after the exchange. */
     /* column-split layout: only the shared leading slice has contributions from other ranks */
@@ -471,7 +472,7 @@ void OSQPMatrix_col_norm_inf(const OSQPMatrix* M, OSQPVectorf* E) {
   else {
     b200_csr_row_absmax(M->St, E->d_val);
     /* row-sharded A: a column's norm is the max over the ranks' row blocks */
-    if (b200_dist_world() > 1 && b200_dist_mlocal >= 0)
+    if (b200_dist_world() > 1 && b200_dist_mlocal >= 0 && M->m == b200_dist_mlocal)
       b200_dist_allreduce_max(E->d_val, b200_dist_nshared >= 0 ? (int)b200_dist_nshared : (int)E->length);
   }
 }

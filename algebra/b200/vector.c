@@ -19,6 +19,7 @@ OSQPVectorf* OSQPVectorf_malloc(OSQPInt length) {
   if (!b) return OSQP_NULL;
   b->length  = length;
   b->is_view = 0;
+  b->shard   = B200_SHARD_OF(length);
   b->d_val   = (OSQPFloat*)b200_malloc((size_t)length * sizeof(OSQPFloat));
   if (!b->d_val) {
     c_free(b);
@@ -32,6 +33,7 @@ OSQPVectorf* OSQPVectorf_calloc(OSQPInt length) {
   if (!b) return OSQP_NULL;
   b->length  = length;
   b->is_view = 0;
+  b->shard   = B200_SHARD_OF(length);
   b->d_val   = (OSQPFloat*)b200_calloc((size_t)length * sizeof(OSQPFloat));
   if (!b->d_val) {
     c_free(b);
@@ -44,6 +46,7 @@ OSQPVectori* OSQPVectori_malloc(OSQPInt length) {
   OSQPVectori* b = (OSQPVectori*)c_malloc(sizeof(OSQPVectori));
   if (!b) return OSQP_NULL;
   b->length = length;
+  b->shard  = B200_SHARD_OF(length);
   b->d_val  = (OSQPInt*)b200_malloc((size_t)length * sizeof(OSQPInt));
   if (!b->d_val) {
     c_free(b);
@@ -56,6 +59,7 @@ OSQPVectori* OSQPVectori_calloc(OSQPInt length) {
   OSQPVectori* b = (OSQPVectori*)c_malloc(sizeof(OSQPVectori));
   if (!b) return OSQP_NULL;
   b->length = length;
+  b->shard  = B200_SHARD_OF(length);
   b->d_val  = (OSQPInt*)b200_calloc((size_t)length * sizeof(OSQPInt));
   if (!b->d_val) {
     c_free(b);
@@ -80,7 +84,10 @@ OSQPVectori* OSQPVectori_new(const OSQPInt* a, OSQPInt length) {
 
 OSQPVectorf* OSQPVectorf_copy_new(const OSQPVectorf* a) {
   OSQPVectorf* b = OSQPVectorf_malloc(a->length);
-  if (b) OSQPVectorf_copy(b, a);
+  if (b) {
+    b->shard = a->shard;      /* a copy is laid out like its source */
+    OSQPVectorf_copy(b, a);
+  }
   return b;
 }
 
@@ -104,6 +111,7 @@ OSQPVectorf* OSQPVectorf_view(const OSQPVectorf* a, OSQPInt head, OSQPInt length
   if (view) {
     view->length  = length;
     view->is_view = 1;
+    view->shard   = B200_SHARD_OF(length);   /* xtilde / ztilde inside xz_tilde: columns / rows */
     view->d_val   = a->d_val + head;
   }
   return view;
@@ -111,6 +119,7 @@ OSQPVectorf* OSQPVectorf_view(const OSQPVectorf* a, OSQPInt head, OSQPInt length
 
 void OSQPVectorf_view_update(OSQPVectorf* a, const OSQPVectorf* b, OSQPInt head, OSQPInt length) {
   a->length = length;
+  a->shard  = B200_SHARD_OF(length);
   a->d_val  = b->d_val + head;
 }
 
@@ -244,16 +253,17 @@ OSQPInt b200_dist_nglobal = -1;
 /* Reductions over row-sharded vectors are combined across ranks inside the kernel library.  Over a
  * column-split vector a rank other than 0 skips the replicated leading slice: `expr` must address
  * its operands through RED_OFF / RED_CNT. */
-#define DIST_REDUCE(len, expr)                                          \
+#define DIST_REDUCE(vec, expr)                                          \
   do {                                                                  \
-    OSQPInt RED_OFF = 0, RED_CNT = (len);                               \
-    int     split_  = B200_IS_COLSPLIT(len);                            \
+    OSQPInt RED_OFF = 0, RED_CNT = (vec)->length;                       \
+    int     dist_   = b200_dist_world() > 1;                            \
+    int     split_  = dist_ && (vec)->shard == B200_SHARD_COLSPLIT;     \
     if (split_ && b200_dist_rank() > 0) {                               \
       RED_OFF = b200_dist_nshared;                                      \
-      RED_CNT = (len) - RED_OFF;                                        \
+      RED_CNT = (vec)->length - RED_OFF;                                \
     }                                                                   \
     (void)RED_OFF; (void)RED_CNT;                                       \
-    if (B200_IS_SHARDED(len) || split_) {                               \
+    if ((dist_ && (vec)->shard == B200_SHARD_ROWS) || split_) {         \
       b200_dist_scope(1);                                               \
       expr;                                                             \
       b200_dist_scope(0);                                               \
@@ -318,7 +328,7 @@ OSQPFloat OSQPVectorf_norm_inf(const OSQPVectorf* v) {
   OSQPFloat cached;
   int       live = b200_norm_cache_live();
   if (b200_norm_cache_get(OSQP_NULL, v->d_val, &cached)) return cached;
-  DIST_REDUCE(v->length, cached = b200_vec_norm_inf(v->d_val + RED_OFF, RED_CNT));
+  DIST_REDUCE(v, cached = b200_vec_norm_inf(v->d_val + RED_OFF, RED_CNT));
   b200_norm_cache_after(live, OSQP_NULL, 0);     /* a reduction writes no vector */
   return cached;
 }
@@ -327,23 +337,23 @@ OSQPFloat OSQPVectorf_scaled_norm_inf(const OSQPVectorf* S, const OSQPVectorf* v
   OSQPFloat cached;
   int       live = b200_norm_cache_live();
   if (b200_norm_cache_get(S->d_val, v->d_val, &cached)) return cached;
-  DIST_REDUCE(v->length, cached = b200_vec_scaled_norm_inf(S->d_val + RED_OFF, v->d_val + RED_OFF, RED_CNT));
+  DIST_REDUCE(v, cached = b200_vec_scaled_norm_inf(S->d_val + RED_OFF, v->d_val + RED_OFF, RED_CNT));
   b200_norm_cache_after(live, OSQP_NULL, 0);
   return cached;
 }
 
 OSQPFloat OSQPVectorf_norm_inf_diff(const OSQPVectorf* a, const OSQPVectorf* b) {
   OSQPFloat r;
-  DIST_REDUCE(a->length, r = b200_vec_norm_inf_diff(a->d_val + RED_OFF, b->d_val + RED_OFF, RED_CNT));
+  DIST_REDUCE(a, r = b200_vec_norm_inf_diff(a->d_val + RED_OFF, b->d_val + RED_OFF, RED_CNT));
   return r;
 }
 
 OSQPFloat OSQPVectorf_norm_1(const OSQPVectorf* a) {
   OSQPFloat r;
-  DIST_REDUCE(a->length, r = b200_vec_norm_1(a->d_val + RED_OFF, RED_CNT));
+  DIST_REDUCE(a, r = b200_vec_norm_1(a->d_val + RED_OFF, RED_CNT));
   /* the only caller (scaling.c:123-124) divides by the LOCAL n to get a mean over columns: hand it
      the global sum rescaled so that the quotient is the global mean */
-  if (B200_IS_COLSPLIT(a->length) && b200_dist_nglobal > 0)
+  if (b200_dist_world() > 1 && a->shard == B200_SHARD_COLSPLIT && b200_dist_nglobal > 0)
     r = r * (OSQPFloat)a->length / (OSQPFloat)b200_dist_nglobal;
   return r;
 }
@@ -353,7 +363,7 @@ OSQPFloat OSQPVectorf_norm_2(const OSQPVectorf* a) { return b200_vec_norm_2(a->d
 OSQPFloat OSQPVectorf_dot_prod(const OSQPVectorf* a, const OSQPVectorf* b) {
   OSQPFloat r;
   int       live = b200_norm_cache_live();
-  DIST_REDUCE(a->length, r = b200_vec_dot(a->d_val + RED_OFF, b->d_val + RED_OFF, RED_CNT));
+  DIST_REDUCE(a, r = b200_vec_dot(a->d_val + RED_OFF, b->d_val + RED_OFF, RED_CNT));
   b200_norm_cache_after(live, OSQP_NULL, 0);
   return r;
 }
@@ -361,14 +371,14 @@ OSQPFloat OSQPVectorf_dot_prod(const OSQPVectorf* a, const OSQPVectorf* b) {
 OSQPFloat OSQPVectorf_dot_prod_signed(const OSQPVectorf* a, const OSQPVectorf* b, OSQPInt sign) {
   OSQPFloat r;
   int       live = b200_norm_cache_live();
-  DIST_REDUCE(a->length, r = b200_vec_dot_signed(a->d_val + RED_OFF, b->d_val + RED_OFF, (int)sign, RED_CNT));
+  DIST_REDUCE(a, r = b200_vec_dot_signed(a->d_val + RED_OFF, b->d_val + RED_OFF, (int)sign, RED_CNT));
   b200_norm_cache_after(live, OSQP_NULL, 0);
   return r;
 }
 
 OSQPInt OSQPVectorf_all_leq(const OSQPVectorf* l, const OSQPVectorf* u) {
   OSQPInt r;
-  DIST_REDUCE(l->length, r = b200_vec_all_leq(l->d_val, u->d_val, l->length));
+  DIST_REDUCE(l, r = b200_vec_all_leq(l->d_val, u->d_val, l->length));
   return r;
 }
 
@@ -376,7 +386,7 @@ OSQPInt OSQPVectorf_in_reccone(const OSQPVectorf* y, const OSQPVectorf* l, const
                                OSQPFloat infval, OSQPFloat tol) {
   OSQPInt r;
   int     live = b200_norm_cache_live();
-  DIST_REDUCE(y->length, r = b200_vec_in_reccone(y->d_val, l->d_val, u->d_val, infval, tol, y->length));
+  DIST_REDUCE(y, r = b200_vec_in_reccone(y->d_val, l->d_val, u->d_val, infval, tol, y->length));
   b200_norm_cache_after(live, OSQP_NULL, 0);
   return r;
 }
@@ -384,7 +394,7 @@ OSQPInt OSQPVectorf_in_reccone(const OSQPVectorf* y, const OSQPVectorf* l, const
 OSQPInt OSQPVectorf_ew_bounds_type(OSQPVectori* iseq, const OSQPVectorf* l, const OSQPVectorf* u,
                                    OSQPFloat tol, OSQPFloat infval) {
   OSQPInt r;
-  DIST_REDUCE(iseq->length,
+  DIST_REDUCE(iseq,
               r = b200_vec_bounds_type(iseq->d_val, l->d_val, u->d_val, tol, infval, iseq->length));
   return r;
 }
