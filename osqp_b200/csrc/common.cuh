@@ -119,8 +119,9 @@ bool mail_wait(unsigned long long seq);
 constexpr int    kXchgMaxWorld     = 8;
 constexpr int    kXchgCap          = 1 << 17;                                  // doubles per vector slot
 constexpr size_t kXchgFlagOff      = (size_t)2 * kXchgMaxWorld * kXchgCap;      // 2 x 8 vector sequence words
-constexpr size_t kXchgScOff        = kXchgFlagOff + 2 * kXchgMaxWorld;          // 2 x 8 x 4 scalar payload
-constexpr size_t kXchgScFlagOff    = kXchgScOff + 2 * kXchgMaxWorld * 4;        // 2 x 8 scalar sequence words
+constexpr int    kXchgScSlot       = 32;                                        // doubles per scalar slot
+constexpr size_t kXchgScOff        = kXchgFlagOff + 2 * kXchgMaxWorld;          // 2 x 8 x 32 scalar payload
+constexpr size_t kXchgScFlagOff    = kXchgScOff + 2 * kXchgMaxWorld * kXchgScSlot;   // 2 x 8 scalar sequence words
 constexpr size_t kXchgTotalDoubles = kXchgScFlagOff + 2 * kXchgMaxWorld + 16;
 struct XchgState {            // device memory behind the buffer; identical on all ranks by construction
   unsigned long long vseq, sseq;   // vector / scalar exchanges completed so far
@@ -135,10 +136,16 @@ struct XchgView {
 };
 __host__ __device__ inline size_t xchg_vec(int set, int r) { return ((size_t)set * kXchgMaxWorld + r) * kXchgCap; }
 __host__ __device__ inline size_t xchg_vflag(int set, int r) { return kXchgFlagOff + (size_t)set * kXchgMaxWorld + r; }
-__host__ __device__ inline size_t xchg_sc(int set, int r) { return kXchgScOff + ((size_t)set * kXchgMaxWorld + r) * 4; }
+__host__ __device__ inline size_t xchg_sc(int set, int r) { return kXchgScOff + ((size_t)set * kXchgMaxWorld + r) * kXchgScSlot; }
 __host__ __device__ inline size_t xchg_scflag(int set, int r) { return kXchgScFlagOff + (size_t)set * kXchgMaxWorld + r; }
 bool dist_p2p_ready();
 const XchgView& dist_xchg_view();
+// dist.cu: combine `count` (<= kXchgScSlot) device scalars over the ranks through peer memory: entry k is
+// summed (bit k of max_mask clear) or maximised (set) over the ranks in rank order when bit k of
+// active_mask is set, left alone otherwise; the result goes back to d_vals and, when d_mail != nullptr, to
+// the mapped host mailbox with sequence number `seq`.  false: peer path unavailable (caller uses NCCL).
+bool dist_p2p_small(double* d_vals, int count, unsigned max_mask, unsigned active_mask, double* d_mail,
+                    unsigned long long seq);
 
 // dist.cu
 bool dist_active();

@@ -5,9 +5,11 @@
 // by BASELINE.json north_star / SURVEY.md section 8e.  NCCL is dlopen'ed so that the single-GPU
 // library has no dependency on it; in a torch process the already-loaded libnccl.so.2 is reused.
 #include "common.cuh"
+#include "xchg.cuh"
 
 #include <dlfcn.h>
 #include <cstring>
+#include <cstdlib>
 
 using namespace b200;
 
@@ -106,11 +108,129 @@ struct P2P {
 P2P p2p;
 }  // namespace
 
+namespace {
+// ONE CTA: `count` scalars of this rank go into slot `rank` of every peer, the peers' come back, entry k is
+// folded over the ranks in rank order (sum / max), the result is written back and posted to the host
+// mailbox.  Shares the scalar slots and their sequence counter with the CG loop's scalar exchange
+// (pcg_graph.cu): every rank issues the same exchanges in the same stream order.
+__global__ void __launch_bounds__(64) g_xchg_small(XchgView X, double* vals, int count, unsigned max_mask,
+                                                   unsigned active_mask, double* mail, unsigned long long mseq) {
+  __shared__ double mine[kXchgScSlot], res[kXchgScSlot];
+  XchgState* S = X.state;
+  const int tid = threadIdx.x, me = X.rank, world = X.world;
+  if (tid < count) mine[tid] = vals[tid];
+  __syncthreads();
+  const unsigned long long seq = *(volatile unsigned long long*)&S->sseq + 1;
+  const int set = (int)(seq & 1ull);
+  if (tid < world && tid != me) {
+    double* dst = X.peer[tid] + xchg_sc(set, me);
+    for (int k = 0; k < count; k++) dst[k] = mine[k];
+    __threadfence_system();
+    st_release_sys((unsigned long long*)(X.peer[tid] + xchg_scflag(set, me)), seq);
+    if (!xchg_wait(S, (const unsigned long long*)(X.mine + xchg_scflag(set, tid)), seq)) S->err = 1;
+  }
+  __syncthreads();
+  if (tid < count) {
+    double a = mine[tid];
+    if ((active_mask >> tid) & 1u) {
+      const bool is_max = (max_mask >> tid) & 1u;
+      a = 0.0;
+      for (int r = 0; r < world; r++) {
+        const double v = (r == me) ? mine[tid] : __ldcg(X.mine + xchg_sc(set, r) + tid);
+        a = is_max ? fmax(a, v) : a + v;
+      }
+    }
+    vals[tid] = a;
+    res[tid] = a;
+  }
+  __syncthreads();
+  if (tid == 0) {
+    S->sseq = seq;
+    if (mail) mail_post(mail, res, count, mseq);
+  }
+}
+
+// the first `n` entries of `buf` summed (or maximised) over the ranks, in place, folded in rank order; same
+// protocol as g_xchg_vector of the CG loop (vector slots, vseq).  The grid must be co-resident.
+template <bool IS_MAX>
+__global__ void __launch_bounds__(kBlock) g_xchg_plain(XchgView X, T* buf, int n) {
+  __shared__ int s_last;
+  XchgState* S = X.state;
+  const int me = X.rank, world = X.world;
+  const unsigned long long seq = *(volatile unsigned long long*)&S->vseq + 1;
+  const int set = (int)(seq & 1ull);
+  const int gtid = blockIdx.x * blockDim.x + threadIdx.x, gstride = gridDim.x * blockDim.x;
+  for (int q = 0; q < world; q++) {
+    if (q == me) continue;
+    double* dst = X.peer[q] + xchg_vec(set, me);
+    for (int i = gtid; i < n; i += gstride) dst[i] = (double)buf[i];
+  }
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) s_last = (atomicAdd(&S->ticket, 1u) == gridDim.x - 1);
+  __syncthreads();
+  if (s_last) {
+    __threadfence_system();
+    if ((int)threadIdx.x < world && (int)threadIdx.x != me)
+      st_release_sys((unsigned long long*)(X.peer[threadIdx.x] + xchg_vflag(set, me)), seq);
+    if (threadIdx.x == 0) S->ticket = 0;
+  }
+  if ((int)threadIdx.x < world && (int)threadIdx.x != me) {
+    if (!xchg_wait(S, (const unsigned long long*)(X.mine + xchg_vflag(set, threadIdx.x)), seq)) S->err = 1;
+  }
+  __syncthreads();
+  for (int i = gtid; i < n; i += gstride) {
+    double a = 0.0;
+    for (int r = 0; r < world; r++) {
+      const double v = (r == me) ? (double)buf[i] : __ldcg(X.mine + xchg_vec(set, r) + i);
+      a = IS_MAX ? fmax(a, v) : a + v;
+    }
+    buf[i] = (T)a;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    if (atomicAdd(&S->ticket2, 1u) == gridDim.x - 1) {   // every CTA has read vseq and folded its part
+      S->ticket2 = 0;
+      S->vseq = seq;
+    }
+  }
+}
+
+// peer path for a vector head; false when unavailable
+template <bool IS_MAX>
+bool p2p_vector(T* d_buf, int n);
+}  // namespace
+
 namespace b200 {
 XchgView g_xchg_view;
 bool dist_p2p_ready() { return p2p.ready && dist_active() && g.world <= kXchgMaxWorld; }
+static bool p2p_outside_loop() {
+  static const bool off = getenv("B200_DIST_NO_P2P") != nullptr || getenv("B200_DIST_P2P_LOOP_ONLY") != nullptr;
+  return dist_p2p_ready() && !off;
+}
+bool dist_p2p_small(double* d_vals, int count, unsigned max_mask, unsigned active_mask, double* d_mail,
+                    unsigned long long seq) {
+  if (!p2p_outside_loop() || count <= 0 || count > kXchgScSlot) return false;
+  g_xchg_small<<<1, 64, 0, ctx().stream>>>(g_xchg_view, d_vals, count, max_mask, active_mask, d_mail, seq);
+  count_launch("xchg(small)");
+  return true;
+}
 const XchgView& dist_xchg_view() { return g_xchg_view; }
 }  // namespace b200
+
+namespace {
+template <bool IS_MAX>
+bool p2p_vector(T* d_buf, int n) {
+  if (!p2p_outside_loop() || n + 8 > kXchgCap) return false;
+  int grid = (n + kBlock * 2 - 1) / (kBlock * 2);
+  if (grid > ctx().sm_count) grid = ctx().sm_count;
+  if (grid < 1) grid = 1;
+  g_xchg_plain<IS_MAX><<<grid, kBlock, 0, ctx().stream>>>(g_xchg_view, d_buf, n);
+  count_launch("xchg(plain vector)");
+  return true;
+}
+}  // namespace
 
 static void p2p_release() {
   if (!p2p.mine) return;
@@ -165,6 +285,7 @@ int  b200_dist_n_shared(void) { return g.n_shared; }
 void b200_dist_allreduce_sum(T* d_buf, int n) {
   if (!dist_active() || n <= 0) return;
   ctx().epoch++;
+  if (p2p_vector<false>(d_buf, n)) return;
   nccl_ok(g.allreduce(d_buf, d_buf, (size_t)n, sizeof(T) == 8 ? NCCL_DOUBLE : NCCL_FLOAT, NCCL_SUM, g.comm,
                       ctx().stream), "ncclAllReduce(sum)");
   if (ctx().trace_on) trace_point("allreduce(vector sum)");
@@ -175,6 +296,7 @@ void b200_dist_allreduce_sum(T* d_buf, int n) {
 void b200_dist_allreduce_max(T* d_buf, int n) {
   if (!dist_active() || n <= 0) return;
   ctx().epoch++;
+  if (p2p_vector<true>(d_buf, n)) return;
   nccl_ok(g.allreduce(d_buf, d_buf, (size_t)n, sizeof(T) == 8 ? NCCL_DOUBLE : NCCL_FLOAT, NCCL_MAX, g.comm,
                       ctx().stream), "ncclAllReduce(max)");
   if (ctx().trace_on) trace_point("allreduce(vector max)");

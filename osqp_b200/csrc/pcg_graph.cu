@@ -14,6 +14,7 @@
 // Grid-wide scalars: every CTA publishes a partial, the LAST CTA to arrive (integer ticket) folds
 // them in index order -> deterministic.
 #include "pcg.cuh"
+#include "xchg.cuh"
 
 #include <cstring>
 #include <cstdlib>
@@ -121,32 +122,6 @@ __constant__ PcgArgs c_args[kMaxContexts];   // one block per library context (h
 
 // ---- peer-memory exchange (row-sharded solve; buffers and protocol: common.cuh / dist.cu) -------------
 __constant__ XchgView c_xchg;
-constexpr unsigned long long kXchgTimeoutNs = 4ull * 1000ull * 1000ull * 1000ull;   // a peer that never arrives
-
-__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
-  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
-}
-__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
-  unsigned long long v;
-  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
-  return v;
-}
-__device__ __forceinline__ unsigned long long globaltimer_ns() {
-  unsigned long long t;
-  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-  return t;
-}
-// spin until the sequence word reaches `seq` (written by a peer over NVLink); bounded, so that a rank
-// whose peer died reports an error instead of hanging the GPU
-__device__ __forceinline__ bool xchg_wait(const unsigned long long* flag, unsigned long long seq) {
-  if (*(volatile int*)&c_xchg.state->err) return false;     // already failed once: never wait again
-  const unsigned long long t0 = globaltimer_ns();
-  unsigned spins = 0;
-  while (ld_acquire_sys(flag) < seq) {
-    if ((++spins & 1023u) == 0 && globaltimer_ns() - t0 > kXchgTimeoutNs) return false;
-  }
-  return true;
-}
 // ALL threads of ONE CTA: this rank's (a, b) goes to every peer, the peers' pairs come back; returns
 // the sum of the a's and the maximum of the b's, folded in rank order (bit-identical on all ranks)
 __device__ __forceinline__ void xchg_scalars(double a_loc, double b_loc, double& a_sum, double& b_max) {
@@ -161,7 +136,7 @@ __device__ __forceinline__ void xchg_scalars(double a_loc, double b_loc, double&
     dst[1] = b_loc;
     __threadfence_system();
     st_release_sys((unsigned long long*)(X.peer[tid] + xchg_scflag(set, me)), seq);
-    if (!xchg_wait((const unsigned long long*)(X.mine + xchg_scflag(set, tid)), seq)) S->err = 1;
+    if (!xchg_wait(S, (const unsigned long long*)(X.mine + xchg_scflag(set, tid)), seq)) S->err = 1;
   }
   __syncthreads();
   double s = 0.0, mx = 0.0;
@@ -478,7 +453,7 @@ __global__ void __launch_bounds__(kBlock) g_xchg_vector(int slot, PcgRun* run, d
     if (threadIdx.x == 0) S->ticket = 0;
   }
   if ((int)threadIdx.x < world && (int)threadIdx.x != me) {
-    if (!xchg_wait((const unsigned long long*)(X.mine + xchg_vflag(set, threadIdx.x)), seq)) S->err = 1;
+    if (!xchg_wait(S, (const unsigned long long*)(X.mine + xchg_vflag(set, threadIdx.x)), seq)) S->err = 1;
   }
   __syncthreads();
   double acc0 = 0.0, acc1 = 0.0, acc2 = 0.0;

@@ -92,6 +92,15 @@ inline double run_reduce(int n, F f) {
   }
   reduce_kernel<OP><<<grid, kBlock, 0, c.stream>>>(n, f, c.d_partials, c.d_ticket, c.d_scalar, nullptr, 0ull);
   count_launch();
+  {
+    // row-sharded operand: combine over the ranks -- through peer memory (one tiny kernel that also
+    // posts the host mailbox) when available, else NCCL + copy + stream synchronisation
+    const unsigned long long seq = c.mail_seq + 1;
+    if (dist_p2p_small(c.d_scalar, 1, OP == RED_MAX ? 1u : 0u, 1u, c.d_mail, seq)) {
+      c.mail_seq = seq;
+      return mail_wait(seq) ? c.h_mail[0] : 0.0;
+    }
+  }
   dist_allreduce_f64(c.d_scalar, 1, OP == RED_MAX);   // row-sharded operand
   B200_CHECK(cudaMemcpyAsync(c.h_scalar, c.d_scalar, sizeof(double), cudaMemcpyDeviceToHost, c.stream));
   B200_CHECK(cudaStreamSynchronize(c.stream));
@@ -414,7 +423,22 @@ extern "C" void b200_admm_residuals(const T* x, const T* y, const T* z, const T*
   count_launch();
   if (dist_active()) {
     // slots 0..5 are maxima over the row-sharded m-vectors, slot 6 (support function) a sum over
-    // them; the n-vector slots are replicated and identical on every rank
+    // them; the n-vector slots are replicated and identical on every rank (plain row layout) or partial
+    // too (column-split layout).  One peer-memory exchange of the 17 scalars when available ...
+    unsigned max_mask = 0, active = 0;
+    for (int s = 0; s < B200_RES_COUNT; s++) {
+      if (!(s == B200_RES_SC || s == B200_RES_XPX || s == B200_RES_QX)) max_mask |= 1u << s;
+      if (s <= B200_RES_SC || dist_split()) active |= 1u << s;
+    }
+    const unsigned long long seq = c.mail_seq + 1;
+    if (dist_p2p_small(c.d_scalar, B200_RES_COUNT, max_mask, active, c.d_mail, seq)) {
+      c.mail_seq = seq;
+      if (mail_wait(seq)) {
+        for (int s = 0; s < B200_RES_COUNT; s++) h_out[s] = c.h_mail[s];
+        return;
+      }
+    }
+    // ... else four NCCL all-reduces
     dist_allreduce_f64(c.d_scalar + B200_RES_PRIM_S, B200_RES_SC - B200_RES_PRIM_S, true);
     dist_allreduce_f64(c.d_scalar + B200_RES_SC, 1, false);
     if (dist_split()) {

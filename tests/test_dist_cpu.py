@@ -229,3 +229,84 @@ def test_bench_reference_arm_line_contract():
     assert d["e2e"]["value"] == d["value"] and d["e2e"]["unit"] == d["unit"]
     assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
     assert "workload" in d["config"]
+
+
+@pytest.mark.parametrize("world", [2, 3, 5])
+@pytest.mark.parametrize("family", ["svm", "huber"])
+def test_block_seeded_shards_reassemble_to_the_world_size_1_problem(family, world):
+    """bench.py's sharded workload: the global QP is defined by seeded sample blocks, so the shards of
+    any world size put together are exactly the problem a single rank generates, every shard is the
+    [rows of the rank] x [shared ; owned] slice of it, and only the features are shared."""
+    gen = {"svm": problems.svm_shard, "huber": problems.huber_shard}[family]
+    kw = dict(n_features=40, n_samples=3000, density=0.05, seed=1, block=256)
+    whole = gen(0, 1, **kw)
+    shards = [gen(r, world, **kw) for r in range(world)]
+    g = problems.assemble_shards(shards)
+    for key in ("P", "A"):
+        d = sp.csc_matrix(whole[key]) - g[key]
+        assert d.nnz == 0 or abs(d).max() == 0
+    for key in ("q", "l", "u"):
+        assert np.array_equal(whole[key], g[key])
+    Aw = sp.csc_matrix(whole["A"]).tocsr()
+    seen_rows = np.concatenate([s["rows"] for s in shards])
+    assert np.array_equal(np.sort(seen_rows), np.arange(whole["A"].shape[0]))          # every row has one home
+    owned = np.concatenate([s["cols"][s["n_shared"]:] for s in shards])
+    assert np.array_equal(np.sort(np.concatenate([shards[0]["cols"][:shards[0]["n_shared"]], owned])),
+                          np.arange(whole["A"].shape[1]))                               # so has every column
+    for s in shards:
+        assert s["n_shared"] == 40 and s["A"].shape[0] != s["A"].shape[1]
+        sub = Aw[s["rows"]][:, s["cols"]]
+        assert abs(sub - s["A"]).max() == 0
+        # a rank's rows touch no column owned by another rank
+        mask = np.ones(whole["A"].shape[1], dtype=bool)
+        mask[s["cols"]] = False
+        assert Aw[s["rows"]][:, np.nonzero(mask)[0]].nnz == 0
+
+
+PEER_WORKER = textwrap.dedent("""
+    import os, sys
+    sys.path.insert(0, {root!r})
+    import torch.distributed as dist
+    from osqp_b200.devmem import kernels
+    from osqp_b200.dist import ShardedOSQP, enable_peer_exchange
+    dist.init_process_group("gloo")
+    k = kernels("f64")
+    # no CUDA device here: the export fails on every rank, the handshake must end in a consistent "no"
+    assert enable_peer_exchange(k, dist) is False
+    os.environ["B200_DIST_NO_P2P"] = "1"
+    assert enable_peer_exchange(k, dist) is False
+    for bad in (dict(polishing=1), dict(time_limit=1.0), dict(adaptive_rho=2)):
+        try:
+            ShardedOSQP._check_settings(bad)
+        except ValueError:
+            continue
+        raise AssertionError(f"{{bad}} accepted in the row-sharded mode")
+    ShardedOSQP._check_settings(dict(adaptive_rho=1, eps_abs=1e-3))
+    dist.barrier()
+    if dist.get_rank() == 0:
+        print("PEER_WORKER_OK")
+    dist.destroy_process_group()
+""")
+
+
+def test_gloo_peer_exchange_handshake_and_settings_guard(tmp_path):
+    script = tmp_path / "peer_worker.py"
+    script.write_text(PEER_WORKER.format(root=str(ROOT)))
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1")
+    env.pop("B200_DIST_NO_P2P", None)
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                          "--master-addr", "127.0.0.1", "--master-port", "29537", str(script)],
+                         capture_output=True, text=True, env=env, timeout=300)
+    assert "PEER_WORKER_OK" in out.stdout, out.stdout[-2000:] + out.stderr[-2000:]
+
+
+def test_bench_reference_arm_follows_the_arm_workload():
+    """under torchrun the B200 arm solves the sharded SVM: the reference arm must name the same workload"""
+    import json
+    env = dict(os.environ, RANK="0", WORLD_SIZE="1", LOCAL_RANK="0")
+    out = subprocess.run([sys.executable, str(ROOT / "bench.py"), "--impl", "reference", "--steps", "1",
+                          "--warmup", "1"], capture_output=True, text=True, timeout=600, env=env)
+    assert out.returncode == 0, out.stderr[-2000:]
+    d = json.loads([l for l in out.stdout.splitlines() if l.strip()][0])
+    assert d["impl"] == "reference" and d["scaling"] == "strong" and "svm" in d["config"]["workload"]
+    assert d["cpu_baseline"]["cores"] == 1 and d["e2e"]["value"] == d["value"]

@@ -5,6 +5,8 @@ TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 
 ( time timeout 300 $TR tools/sharded_worker.py --family svm --scale 0.003 --check --blocks ) > gpurun_out/r2c7_worker_svm8.log 2>&1
 grep -E "SHARDED|REPLICATED" gpurun_out/r2c7_worker_svm8.log | cut -c1-700
 ( time timeout 800 $TR bench.py --gpus 8 --steps 5 --warmup 2 ) > gpurun_out/r2c7_bench_svm_8gpu.json 2> gpurun_out/r2c7_bench_svm_8gpu_err.log
+( time timeout 200 $TR bench.py --gpus 8 --steps 5 --warmup 2 --mode batch --workload mpc ) > gpurun_out/r2c7_bench_mpc_batch_8gpu.json 2> gpurun_out/r2c7_bench_mpc_batch_8gpu_err.log
+cat gpurun_out/r2c7_bench_mpc_batch_8gpu.json | cut -c1-1500
 ( time timeout 600 $TR bench.py --gpus 8 --steps 5 --warmup 2 --workload huber --no-strong-baseline ) > gpurun_out/r2c7_bench_huber_8gpu.json 2> gpurun_out/r2c7_bench_huber_8gpu_err.log
 python - <<'PY'
 import json
