@@ -46,7 +46,8 @@ def test_two_rank_sharded_solve_matches_oracle(family, layout, exchange):
     assert res["PARITY"] == "OK", res
     # the NCCL path needs 3 collectives per CG iteration and 2 per linear solve for its CG loops alone;
     # what both paths share are the ~6 collectives of a termination check and the setup-time norms
-    cg_loop_calls = 3 * res["cg_iters"] + 2 * res["solves"]
+    # (plain row blocks: the n-vectors are replicated, one vector all-reduce per K p is all it takes)
+    cg_loop_calls = 3 * res["cg_iters"] + 2 * res["solves"] if layout == "split" else res["cg_iters"]
     if exchange == "p2p":
         assert res["p2p"] is True and res["graph_launches"] >= res["solves"], res   # the loop ran as a CUDA graph
         assert res["allreduce_calls"] < cg_loop_calls, res       # no collective inside the CG loop
