@@ -6,6 +6,8 @@
  * where two suffice.  auxil.c stays BYTE-IDENTICAL: the Makefile compiles it with
  *     -Dupdate_xz_tilde=osqp_ref_update_xz_tilde -Dupdate_x=osqp_ref_update_x
  *     -Dupdate_z=osqp_ref_update_z -Dupdate_y=osqp_ref_update_y -Dupdate_info=osqp_ref_update_info
+ *     -Dcheck_termination=osqp_ref_check_termination   (the macro also renames the OSQPSettings field of
+ *      that name inside this one translation unit -- consistently, so the layout is untouched)
  * so that the reference definitions keep existing under the osqp_ref_ names (and can be selected
  * at run time with OSQP_B200_UNFUSED=1 for A/B parity runs), while the calls made by
  * src/osqp_api.c:708-726 bind to the versions below.  Expression order follows the reference's
@@ -25,6 +27,10 @@ void osqp_ref_update_x(OSQPSolver* solver);
 void osqp_ref_update_z(OSQPSolver* solver);
 void osqp_ref_update_y(OSQPSolver* solver);
 void osqp_ref_update_info(OSQPSolver* solver, OSQPInt iter, OSQPInt polishing);
+OSQPInt osqp_ref_check_termination(OSQPSolver* solver, OSQPInt approximate);
+/* non-static in the unmodified auxil.c (src/auxil.c:460,520), not declared in auxil.h */
+OSQPInt is_primal_infeasible(OSQPSolver* solver, OSQPFloat eps_prim_inf);
+OSQPInt is_dual_infeasible(OSQPSolver* solver, OSQPFloat eps_dual_inf);
 
 /* A x carried through the relaxation step: valid from the first exact product of a
  * solve (update_info at iteration 1) until the solve ends; recomputed exactly every
@@ -200,4 +206,114 @@ void update_info(OSQPSolver* solver, OSQPInt iter, OSQPInt polishing) {
     b200_norm_cache_put(work->scaling->Dinv->d_val, work->Px->d_val, work->Px->length, (OSQPFloat)r[B200_RES_PX_U]);
   }
   b200_norm_cache_seal();
+}
+
+
+/* check_termination (auxil.c:808-945), same decisions, fewer host round trips.  The tolerances are
+ * evaluated with the very calls of compute_prim_tol / compute_dual_tol (auxil.c:334-458), which the
+ * norm cache filled by update_info above answers without a kernel.  The infeasibility tests
+ * (auxil.c:460-585) each start with two or three blocking reductions whose values alone decide
+ * whether the test can return non-zero at all: ||delta_y|| > tol and u'dy+ + l'dy- < 0, resp.
+ * ||delta_x|| > tol and q'dx < 0.  Those five scalars come from ONE kernel
+ * (b200_admm_infeas_scalars); only when they leave the outcome open is the reference function
+ * itself called -- it recomputes the same quantities and goes on to the matrix products. */
+OSQPInt check_termination(OSQPSolver* solver, OSQPInt approximate) {
+  OSQPInfo*      info     = solver->info;
+  OSQPSettings*  settings = solver->settings;
+  OSQPWorkspace* work     = solver->work;
+  OSQPFloat eps_abs = settings->eps_abs, eps_rel = settings->eps_rel;
+  OSQPFloat eps_prim_inf = settings->eps_prim_inf, eps_dual_inf = settings->eps_dual_inf;
+  OSQPFloat eps_prim, eps_dual, eps_gap, mx, tmp;
+  OSQPInt   exitflag = 0, prim_ok = 0, dual_ok = 0, gap_ok = 0, prim_inf = 0, dual_inf = 0;
+  int       unscale = settings->scaling && !settings->scaled_termination;
+  int       need_p = 0, need_d = 0;
+  double    f[5];
+
+  if (unfused()) return osqp_ref_check_termination(solver, approximate);
+
+  if ((info->prim_res > OSQP_INFTY) || (info->dual_res > OSQP_INFTY)) {
+    update_status(info, OSQP_NON_CVX);
+    info->obj_val = OSQP_NAN;
+    return 1;
+  }
+  if (approximate) {
+    eps_abs *= 10; eps_rel *= 10; eps_prim_inf *= 10; eps_dual_inf *= 10;
+  }
+
+  /* residual tests (compute_prim_tol / compute_dual_tol) */
+  if (work->data->m == 0) {
+    prim_ok = 1;
+  } else {
+    if (unscale) {
+      mx  = OSQPVectorf_scaled_norm_inf(work->scaling->Einv, work->z);
+      tmp = OSQPVectorf_scaled_norm_inf(work->scaling->Einv, work->Ax);
+    } else {
+      mx  = OSQPVectorf_norm_inf(work->z);
+      tmp = OSQPVectorf_norm_inf(work->Ax);
+    }
+    eps_prim = eps_abs + eps_rel * c_max(mx, tmp);
+    if (info->prim_res < eps_prim) prim_ok = 1;
+    else need_p = 1;
+  }
+  if (unscale) {
+    mx  = OSQPVectorf_scaled_norm_inf(work->scaling->Dinv, work->data->q);
+    tmp = OSQPVectorf_scaled_norm_inf(work->scaling->Dinv, work->Aty);
+    mx  = c_max(mx, tmp);
+    tmp = OSQPVectorf_scaled_norm_inf(work->scaling->Dinv, work->Px);
+    mx  = c_max(mx, tmp) * work->scaling->cinv;
+  } else {
+    mx  = OSQPVectorf_norm_inf(work->data->q);
+    tmp = OSQPVectorf_norm_inf(work->Aty);
+    mx  = c_max(mx, tmp);
+    tmp = OSQPVectorf_norm_inf(work->Px);
+    mx  = c_max(mx, tmp);
+  }
+  eps_dual = eps_abs + eps_rel * mx;
+  if (info->dual_res < eps_dual) dual_ok = 1;
+  else need_d = 1;
+
+  /* infeasibility tests: pre-test from one kernel, the reference function only when it can fire */
+  if (need_p || need_d) {
+    /* writes delta_y only: the norms parked by update_info stay valid for compute_rho_estimate */
+    int live = b200_norm_cache_live();
+    b200_admm_infeas_scalars(work->delta_y->d_val, work->data->l->d_val, work->data->u->d_val,
+                             unscale ? work->scaling->E->d_val : OSQP_NULL, work->delta_x->d_val,
+                             unscale ? work->scaling->D->d_val : OSQP_NULL, work->data->q->d_val,
+                             OSQP_INFTY * OSQP_MIN_SCALING, (int)work->data->n, (int)work->data->m,
+                             need_p, need_d, f);
+    b200_norm_cache_after(live, work->delta_y->d_val, work->delta_y->length);
+    if (need_p && f[0] > OSQP_DIVISION_TOL && (f[1] + f[2]) < 0.0)
+      prim_inf = is_primal_infeasible(solver, eps_prim_inf);
+    if (need_d && f[3] > OSQP_DIVISION_TOL && f[4] < 0.0)
+      dual_inf = is_dual_infeasible(solver, eps_dual_inf);
+  }
+
+  /* duality gap (compute_duality_gap_tol) */
+  if (settings->check_dualgap) {
+    mx = c_absval(work->xtPx);
+    mx = c_max(mx, c_absval(work->qtx));
+    mx = c_max(mx, c_absval(work->SC));
+    if (unscale) mx = work->scaling->cinv * mx;
+    eps_gap = eps_abs + eps_rel * mx;
+    if (unscale) { if (c_absval(info->duality_gap) < eps_gap) gap_ok = 1; }
+    else         { if (c_absval(work->scaled_dual_gap) < eps_gap) gap_ok = 1; }
+  } else {
+    gap_ok = 1;
+  }
+
+  if (prim_ok && dual_ok && gap_ok) {
+    update_status(info, approximate ? OSQP_SOLVED_INACCURATE : OSQP_SOLVED);
+    exitflag = 1;
+  } else if (prim_inf) {
+    update_status(info, approximate ? OSQP_PRIMAL_INFEASIBLE_INACCURATE : OSQP_PRIMAL_INFEASIBLE);
+    if (unscale) OSQPVectorf_ew_prod(work->delta_y, work->delta_y, work->scaling->E);
+    info->obj_val = OSQP_INFTY;
+    exitflag      = 1;
+  } else if (dual_inf) {
+    update_status(info, approximate ? OSQP_DUAL_INFEASIBLE_INACCURATE : OSQP_DUAL_INFEASIBLE);
+    if (unscale) OSQPVectorf_ew_prod(work->delta_x, work->delta_x, work->scaling->D);
+    info->obj_val = -OSQP_INFTY;
+    exitflag      = 1;
+  }
+  return exitflag;
 }

@@ -266,6 +266,15 @@ void b200_admm_residuals(const b200_float* d_x, const b200_float* d_y, const b20
                          const b200_float* d_q, const b200_float* d_l, const b200_float* d_u,
                          const b200_float* d_Einv, const b200_float* d_Dinv, b200_float infval,
                          b200_float deadzone, int n, int m, double* h_out);
+/* The five scalars that decide whether is_primal_infeasible / is_dual_infeasible (src/auxil.c:460-585)
+ * can fire at all -- { ||E.*dy||_inf, u'max(dy,0), l'min(dy,0), ||D.*dx||_inf, q'dx }, dy projected on the
+ * polar of the recession cone in place first -- in one kernel and one host round trip instead of five
+ * blocking reductions per termination check.  d_E / d_D may be NULL. */
+void b200_admm_infeas_scalars(b200_float* d_dy, const b200_float* d_l, const b200_float* d_u,
+                              const b200_float* d_E, const b200_float* d_dx, const b200_float* d_D,
+                              const b200_float* d_q, b200_float infval, int n, int m, int do_primal,
+                              int do_dual, double* h_out);
+
 /* ------------------------------------------------------ batches of small QPs (BASELINE configs[4])
  * nb independent QPs that share P and A (hence the scaling D, E, c of the set-up template problem) and
  * differ in their bounds (and optionally q): ONE CTA per QP runs the whole osqp_solve loop -- ADMM

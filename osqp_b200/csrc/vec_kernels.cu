@@ -453,6 +453,132 @@ extern "C" void b200_admm_residuals(const T* x, const T* y, const T* z, const T*
   for (int s = 0; s < B200_RES_COUNT; s++) h_out[s] = c.h_scalar[s];
 }
 
+// ------------------------------------------------------------- infeasibility pre-tests
+namespace {
+struct InfArgs {
+  T* dy; const T *l, *u, *E, *dx, *D, *q;
+  T infval;
+  int n, m, n_off, do_primal, do_dual;
+};
+// 0: ||E .* proj(dy)||_inf   1: u' max(proj(dy), 0)   2: l' min(proj(dy), 0)   3: ||D .* dx||_inf   4: q' dx
+__global__ void __launch_bounds__(kBlock) infeas_kernel(InfArgs a, double* partials, unsigned* ticket, double* out,
+                                                        double* mail, unsigned long long seq) {
+  __shared__ double shw[5][kBlock / 32];
+  __shared__ bool is_last;
+  double v[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
+  const int stride = gridDim.x * blockDim.x, gtid = blockIdx.x * blockDim.x + threadIdx.x;
+  if (a.do_primal) {
+    for (int j = gtid; j < a.m; j += stride) {
+      // project_polar_reccone in place, exactly as b200_vec_project_polar_reccone
+      T yi = a.dy[j];
+      const T lo = a.l[j], hi = a.u[j];
+      if (hi > +a.infval) {
+        if (lo < -a.infval) yi = (T)0;
+        else yi = (yi < (T)0) ? yi : (T)0;
+      } else if (lo < -a.infval) {
+        yi = (yi > (T)0) ? yi : (T)0;
+      }
+      a.dy[j] = yi;
+      const double y = yi, e = a.E ? (double)a.E[j] : 1.0;
+      v[0] = fmax(v[0], dabs(e * y));
+      v[1] += (double)hi * (y > 0.0 ? y : 0.0);
+      v[2] += (double)lo * (y < 0.0 ? y : 0.0);
+    }
+  }
+  if (a.do_dual) {
+    for (int i = a.n_off + gtid; i < a.n; i += stride) {
+      const double x = a.dx[i], d = a.D ? (double)a.D[i] : 1.0;
+      v[3] = fmax(v[3], dabs(d * x));
+      v[4] += (double)a.q[i] * x;
+    }
+  }
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+#pragma unroll
+  for (int s = 0; s < 5; s++) {
+    const bool is_max = (s == 0 || s == 3);
+    const double r = is_max ? warp_max(v[s]) : warp_sum(v[s]);
+    if (lane == 0) shw[s][w] = r;
+  }
+  __syncthreads();
+  if (threadIdx.x < 5) {
+    const int s = threadIdx.x;
+    const bool is_max = (s == 0 || s == 3);
+    double acc = 0.0;
+    for (int k = 0; k < kBlock / 32; k++) acc = is_max ? fmax(acc, shw[s][k]) : acc + shw[s][k];
+    partials[s * gridDim.x + blockIdx.x] = acc;
+    __threadfence();
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) is_last = (atomicAdd(ticket, 1u) == gridDim.x - 1);
+  __syncthreads();
+  if (is_last) {
+    __threadfence();
+    if (w < 5) {
+      const int s = w;
+      const bool is_max = (s == 0 || s == 3);
+      double acc = 0.0;
+      for (int b = lane; b < gridDim.x; b += 32) {
+        const double p = __ldcg(&partials[s * gridDim.x + b]);
+        acc = is_max ? fmax(acc, p) : acc + p;
+      }
+      acc = is_max ? warp_max(acc) : warp_sum(acc);
+      if (lane == 0) { out[s] = acc; shw[s][0] = acc; }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      *ticket = 0;
+      if (mail) {
+        double vals[5];
+        for (int s = 0; s < 5; s++) vals[s] = shw[s][0];
+        mail_post(mail, vals, 5, seq);
+      }
+    }
+  }
+}
+}  // namespace
+
+// The scalars that decide whether is_primal_infeasible / is_dual_infeasible (src/auxil.c:460-585) can
+// return non-zero at all, in ONE kernel and ONE host round trip instead of five blocking reductions:
+// h_out = { ||E .* dy||_inf, u' max(dy, 0), l' min(dy, 0), ||D .* dx||_inf, q' dx } with dy projected on the
+// polar of the recession cone IN PLACE (as the reference does first).  E / D may be NULL (no scaling or
+// scaled termination).  Row-sharded: combined over the ranks (rows: 0-2; columns: 3-4 when column-split).
+extern "C" void b200_admm_infeas_scalars(T* dy, const T* l, const T* u, const T* E, const T* dx, const T* D,
+                                         const T* q, T infval, int n, int m, int do_primal, int do_dual,
+                                         double* h_out) {
+  Context& c = ctx();
+  InfArgs a{dy, l, u, E, dx, D, q, infval, n, m, dist_col_off(), do_primal, do_dual};
+  const int nm = n > m ? n : m;
+  int grid = ew_grid(nm);
+  if (grid > kMaxRedBlocks) grid = kMaxRedBlocks;
+  if (!dist_active()) {
+    const unsigned long long seq = ++c.mail_seq;
+    infeas_kernel<<<grid, kBlock, 0, c.stream>>>(a, c.d_partials, c.d_ticket, c.d_scalar, c.d_mail, seq);
+    count_launch();
+    if (mail_wait(seq)) {
+      for (int s = 0; s < 5; s++) h_out[s] = c.h_mail[s];
+      return;
+    }
+    for (int s = 0; s < 5; s++) h_out[s] = 0.0;
+    return;
+  }
+  infeas_kernel<<<grid, kBlock, 0, c.stream>>>(a, c.d_partials, c.d_ticket, c.d_scalar, nullptr, 0ull);
+  count_launch();
+  const unsigned active = dist_split() ? 0x1Fu : 0x07u;
+  const unsigned long long seq = c.mail_seq + 1;
+  if (dist_p2p_small(c.d_scalar, 5, 0x09u, active, c.d_mail, seq)) {
+    c.mail_seq = seq;
+    if (mail_wait(seq)) {
+      for (int s = 0; s < 5; s++) h_out[s] = c.h_mail[s];
+      return;
+    }
+  }
+  for (int s = 0; s < 5; s++)
+    if ((active >> s) & 1u) dist_allreduce_f64(c.d_scalar + s, 1, s == 0 || s == 3);
+  B200_CHECK(cudaMemcpyAsync(c.h_scalar, c.d_scalar, sizeof(double) * 5, cudaMemcpyDeviceToHost, c.stream));
+  B200_CHECK(cudaStreamSynchronize(c.stream));
+  for (int s = 0; s < 5; s++) h_out[s] = c.h_scalar[s];
+}
+
 // ------------------------------------------------------------- fused ADMM steps
 // compute_rhs (src/auxil.c:136-158): x~ = sigma x_prev - q ; z~ = z_prev - rho^-1 y
 void b200_admm_compute_rhs(T* xt, T* zt, const T* x_prev, const T* q, const T* z_prev, const T* y,
