@@ -981,7 +981,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true", help="skip cpu_baseline / parity / ref_cuda / same-config blocks")
     ap.add_argument("--no-ref-cuda", action="store_true")
     ap.add_argument("--no-same-config", action="store_true")
-    ap.add_argument("--same-config-budget", type=float, default=240.0,
+    ap.add_argument("--same-config-budget", type=float, default=300.0,
                     help="seconds after which the full-size oracle solve of configs[0] is abandoned")
     ap.add_argument("--no-strong-baseline", action="store_true")
     ap.add_argument("--sharded-e2e-steps", type=int, default=5)

@@ -30,7 +30,11 @@ namespace {
 
 constexpr int kBB = 128;               // threads per CTA (= per QP)
 constexpr int kBW = kBB / 32;
-constexpr double kInfty = 1e30;        // OSQP_INFTY (double and float builds of the reference differ: 1e30 / 1e17)
+#ifdef B200_USE_FLOAT
+constexpr double kInfty = 1e17;        // OSQP_INFTY of a float build (osqp_api_constants.h:196-203)
+#else
+constexpr double kInfty = 1e30;        // OSQP_INFTY
+#endif
 constexpr double kMinScaling = 1e-4;   // OSQP_MIN_SCALING
 constexpr double kDivTol = 1.0 / kInfty;
 constexpr double kRhoMin = 1e-6, kRhoMax = 1e6, kRhoTol = 1e-4, kRhoEqOverIneq = 1e3;

@@ -19,8 +19,11 @@ int b200_build_schedule(b200_csr* M, const int* rp) {
   int r = 0;
   while (r < nrows) {
     const int len = rp[r + 1] - rp[r];
-    if (len > kTile) {
-      // long row: chunk it
+    if (len > kLongRow) {
+      // long row: chunk it.  Rows between kLongRow and kTile entries are "chunked" into ONE chunk: at most
+      // one of them fits a tile anyway, and the per-row group reduction would leave it to a single warp
+      // (<= 32 lanes walk the staged terms while 15 warps wait: 160 -> 1xx us on the operator pass of the
+      // 8-GPU SVM shards, whose feature rows hold 1250 entries); the chunk path sums CTA-wide.
       const int nchunks = (len + kTile - 1) / kTile;
       const int lr      = (int)longs.size();
       longs.push_back(make_int4(r, (int)desc.size(), nchunks, 0));
@@ -35,7 +38,7 @@ int b200_build_schedule(b200_csr* M, const int* rp) {
     int r1 = r, cnt = 0;
     while (r1 < nrows && (r1 - r) < kMaxRows) {
       const int l = rp[r1 + 1] - rp[r1];
-      if (l > kTile || cnt + l > kTile) break;
+      if (l > kLongRow || cnt + l > kTile) break;
       cnt += l;
       r1++;
     }

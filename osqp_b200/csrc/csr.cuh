@@ -45,6 +45,7 @@ namespace b200 {
 constexpr int kSpmvBlock = B200_SPMV_BLOCK;  // threads per CTA of every kernel that runs spmv_pass
 constexpr int kTile      = B200_SPMV_TILE;   // staged nonzeros per CTA pass
 constexpr int kMaxRows   = kTile / 2;        // rows per normal block
+constexpr int kLongRow   = kTile / 2;        // rows with more entries get CTA-wide chunk(s) of their own
 constexpr int kPad       = 8;      // slack elements at the end of every matrix array
 
 constexpr int kSmemElems     = kTile + 40;                  // staged terms + reduction scratch

@@ -287,7 +287,10 @@ bool device_scan(int* d_data, int n, int* d_max, cudaStream_t st) {
   int* d_tot = nullptr;
   int* d_dummy = nullptr;
   bool ok = B200_CHECK(dev_malloc(&d_tot, sizeof(int) * ((size_t)nchunks + 1)));
-  if (!d_max) ok &= B200_CHECK(dev_malloc(&d_dummy, sizeof(int)));
+  if (!d_max) {
+    ok &= B200_CHECK(dev_malloc(&d_dummy, sizeof(int)));
+    if (ok) ok &= B200_CHECK(cudaMemsetAsync(d_dummy, 0, sizeof(int), st));   // atomicMax target (initcheck)
+  }
   if (ok) {
     scan_totals<<<nchunks, kScanBlock, 0, st>>>(n, d_data, d_tot, d_max ? d_max : d_dummy);
     count_launch();

@@ -83,6 +83,7 @@ def kernels(precision="f64"):
         "b200_admm_update_xzy": (None, [vp] * 13 + [F, F, F, i, i]),
         "b200_admm_update_xzy_carry": (None, [vp] * 13 + [F, F, F, i, i, vp]),
         "b200_admm_residuals": (None, [vp] * 11 + [F, F, i, i, vp]),
+        "b200_admm_infeas_scalars": (None, [vp] * 7 + [F, i, i, i, i, vp]),
         "b200_epoch": (C.c_ulonglong, []),
     }
     for name, (res, args) in sig.items():

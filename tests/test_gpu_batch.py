@@ -49,7 +49,7 @@ def test_batch_matches_sequential_solves(b200_lib, settings, rho_is_vec):
         # tight: 10 % / 2 check intervals; eps 1e-3 with inexact CG solves: the sequential path carries A x
         # through the CG recurrence, the batch kernel recomputes it -- rounding-level differences move the
         # rho updates by a check interval or two
-        band = max(0.10 * r.info.iter, 2 * st["check_termination"]) if tight else max(0.25 * r.info.iter, 20)
+        band = max(0.10 * r.info.iter, 2 * st["check_termination"]) if tight else max(0.5 * r.info.iter, 20)
         assert abs(int(rb.iter[i]) - r.info.iter) <= band, (i, int(rb.iter[i]), r.info.iter)
     tmpl.cleanup()
 

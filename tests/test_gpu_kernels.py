@@ -68,6 +68,48 @@ def test_fused_rhs_and_update_match_auxil_c(kern, rho_is_vec, n, m):
 
 
 @pytest.mark.parametrize("scaled", [0, 1])
+@pytest.mark.parametrize("do_primal,do_dual", [(1, 1), (1, 0), (0, 1)])
+@pytest.mark.parametrize("n,m", [(13, 29), (300, 70000), (4000, 7)])
+def test_fused_infeasibility_pretest_scalars(kern, scaled, do_primal, do_dual, n, m):
+    """the five scalars that decide whether is_primal_infeasible / is_dual_infeasible (auxil.c:460-585) can
+    fire, from ONE kernel; delta_y is projected on the polar of the recession cone in place only when the
+    primal test is asked for"""
+    k = kern
+    rng = np.random.default_rng(11 * n + m)
+    dy, dx, q = rng.standard_normal(m), rng.standard_normal(n), rng.standard_normal(n)
+    l = rng.standard_normal(m) - 1.0
+    u = l + rng.random(m) * 2
+    l[::3] = -1e30
+    u[1::4] = 1e30
+    E, D = rng.random(m) + 0.5, rng.random(n) + 0.5
+    infval = 1e30 * 1e-4
+    d_dy, d_l, d_u, d_dx, d_q, d_E, d_D = (dev(k, v) for v in (dy, l, u, dx, q, E, D))
+    out = np.full(5, -1.0)
+    k.b200_admm_infeas_scalars(d_dy.ptr, d_l.ptr, d_u.ptr, d_E.ptr if scaled else None, d_dx.ptr,
+                               d_D.ptr if scaled else None, d_q.ptr, infval, n, m, do_primal, do_dual, out.ctypes.data)
+    yp = dy.copy()
+    both = (u > infval) & (l < -infval)
+    yp[both] = 0
+    up = (u > infval) & ~both
+    yp[up] = np.minimum(yp[up], 0)
+    lo = (l < -infval) & ~(u > infval)
+    yp[lo] = np.maximum(yp[lo], 0)
+    Ev, Dv = (E if scaled else np.ones(m)), (D if scaled else np.ones(n))
+    ref = [np.abs(Ev * yp).max(), u @ np.maximum(yp, 0), l @ np.minimum(yp, 0), np.abs(Dv * dx).max(), q @ dx]
+    if do_primal:
+        assert np.array_equal(d_dy.get(), yp)                     # projected in place, bit for bit
+        assert abs(out[0] - ref[0]) <= 1e-12 * ref[0]
+        for s in (1, 2):
+            assert abs(out[s] - ref[s]) <= 1e-9 * max(1.0, abs(ref[s]))
+    else:
+        assert np.array_equal(d_dy.get(), dy) and (out[:3] == 0).all()
+    if do_dual:
+        assert abs(out[3] - ref[3]) <= 1e-12 * ref[3] and abs(out[4] - ref[4]) <= 1e-9 * max(1.0, abs(ref[4]))
+    else:
+        assert (out[3:] == 0).all()
+
+
+@pytest.mark.parametrize("scaled", [0, 1])
 @pytest.mark.parametrize("n,m", [(13, 29), (5000, 1), (300, 70000)])
 def test_fused_residual_reductions(kern, scaled, n, m):
     """every scalar of compute_prim_res / compute_dual_res / compute_obj_val_dual_gap /
