@@ -189,7 +189,7 @@ def test_pcg_reference_known_answer(kern, driver):
 
 
 @pytest.mark.parametrize("driver", ["persistent", "graph"])
-@pytest.mark.parametrize("case", ["scalar_rho", "rho_vec", "polish", "unconstrained", "long_rows"])
+@pytest.mark.parametrize("case", ["scalar_rho", "rho_vec", "polish", "unconstrained", "long_rows", "mid_rows"])
 def test_pcg_against_direct_solve(kern, driver, case):
     k = kern
     rng = np.random.default_rng(3)
@@ -197,6 +197,11 @@ def test_pcg_against_direct_solve(kern, driver, case):
     if case == "long_rows":
         n, m = 6000, 40
         A = sp.random(m, n, density=0.9, format="csr", random_state=4)        # rows of ~5400 entries
+    elif case == "mid_rows":
+        # rows of A between half a tile and a tile (1024 < len <= 2048): single CTA-wide chunks; the columns
+        # of A (rows of A') stay short, so both kinds of tile occur in one solve
+        n, m = 2500, 60
+        A = sp.random(m, n, density=0.6, format="csr", random_state=4)        # rows of ~1500 entries
     elif case == "unconstrained":
         m = 0
         A = sp.csr_matrix((0, n))
