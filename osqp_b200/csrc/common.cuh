@@ -77,7 +77,11 @@ inline cudaError_t dev_malloc(P** p, size_t bytes) {
   return cudaMallocAsync((void**)p, bytes ? bytes : 8, ctx().stream);
 }
 inline void dev_free(void* p) {
-  if (p) cudaFreeAsync(p, ctx().stream);
+  if (!p) return;
+  // a thread without a live library context (e.g. a garbage collector finalising a solver that another
+  // thread created) has no stream to order the release on: cudaFree synchronises instead
+  if (ctx().stream) cudaFreeAsync(p, ctx().stream);
+  else cudaFree(p);
 }
 
 // launch tracer (context.cu): development aid, active only when B200_TRACE_FILE is set

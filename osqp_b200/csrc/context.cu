@@ -178,13 +178,25 @@ int b200_init(int device) {
     fprintf(stderr, "[osqp_b200] more than %d library contexts (host threads with live solvers)\n", kMaxContexts);
     return 1;
   }
+  // every failure from here on gives the slot (and whatever was created) back
+  auto fail = [&]() {
+    if (c.stream) cudaStreamSynchronize(c.stream);
+    dev_free(c.d_partials); dev_free(c.d_ticket); dev_free(c.d_scalar);
+    if (c.h_scalar) cudaFreeHost(c.h_scalar);
+    if (c.h_mail) cudaFreeHost(c.h_mail);
+    if (c.stream) cudaStreamDestroy(c.stream);
+    c.d_partials = nullptr; c.d_ticket = nullptr; c.d_scalar = nullptr; c.h_scalar = nullptr;
+    c.h_mail = c.d_mail = nullptr; c.stream = nullptr;
+    slot_release(c.slot);
+    return 1;
+  };
   cudaDeviceProp prop;
-  if (!B200_CHECK(cudaGetDeviceProperties(&prop, device))) return 1;
+  if (!B200_CHECK(cudaGetDeviceProperties(&prop, device))) return fail();
   c.device   = device;
   c.sm_count = prop.multiProcessorCount;
   snprintf(c.name, sizeof(c.name), "%s (sm_%d%d, %d SMs)", prop.name, prop.major, prop.minor,
            prop.multiProcessorCount);
-  if (!B200_CHECK(cudaStreamCreateWithFlags(&c.stream, cudaStreamNonBlocking))) return 1;
+  if (!B200_CHECK(cudaStreamCreateWithFlags(&c.stream, cudaStreamNonBlocking))) { c.stream = nullptr; return fail(); }
   {
     cudaMemPool_t pool;
     if (B200_CHECK(cudaDeviceGetDefaultMemPool(&pool, device))) {
@@ -198,11 +210,11 @@ int b200_init(int device) {
   ok &= B200_CHECK(dev_malloc(&c.d_scalar, sizeof(double) * kScalarSlots));
   ok &= B200_CHECK(cudaMallocHost(&c.h_scalar, sizeof(double) * kScalarSlots));
   ok &= B200_CHECK(cudaHostAlloc(&c.h_mail, sizeof(double) * (kMailSlots + 1), cudaHostAllocMapped));
-  if (!ok) return 1;
+  if (!ok) return fail();
   memset(c.h_mail, 0, sizeof(double) * (kMailSlots + 1));
   ok &= B200_CHECK(cudaHostGetDevicePointer(&c.d_mail, c.h_mail, 0));
   c.mail_seq = 0;
-  if (!ok) return 1;
+  if (!ok) return fail();
   B200_CHECK(cudaMemsetAsync(c.d_ticket, 0, sizeof(unsigned) * 4, c.stream));
   B200_CHECK(cudaMemsetAsync(c.d_scalar, 0, sizeof(double) * kScalarSlots, c.stream));
   b200_csr_configure_kernels();

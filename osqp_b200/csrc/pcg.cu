@@ -282,6 +282,7 @@ b200_pcg* b200_pcg_create(const b200_csr* P, const b200_csr* A, const b200_csr* 
   Context& c = ctx();
   b200_pcg* s = new b200_pcg();
   s->P = P; s->A = A; s->At = At; s->n = n; s->m = m;
+  s->owner_slot = c.slot;
   bool ok = true;
   auto alloc = [&](T** p, size_t cnt) { ok &= B200_CHECK(dev_malloc(p, sizeof(T) * (cnt + 1))); };
   alloc(&s->d_x, n); alloc(&s->d_p, n); alloc(&s->d_Kp, n); alloc(&s->d_r, n);
@@ -407,6 +408,12 @@ void b200_pcg_warm_start(b200_pcg* s, const T* d_x) {
 int b200_pcg_solve(b200_pcg* s, T* d_b, int admm_iter, double prim_res, double dual_res, int max_iter,
                    double tol_fraction, int reduction_threshold) {
   if (s->n <= 0) return 0;
+  if (ctx().refcount <= 0 || ctx().slot != s->owner_slot) {
+    // the context (stream, constant argument block, mailbox) is per host thread: a solve issued from
+    // another thread would run on the wrong stream against the wrong argument block
+    fprintf(stderr, "[osqp_b200] solver used from a thread other than the one that created it\n");
+    return 1;
+  }
   PcgArgs a;
   memset(&a, 0, sizeof(a));
   a.K2 = s->K2.view();

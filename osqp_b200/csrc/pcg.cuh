@@ -79,6 +79,7 @@ struct b200_pcg {
   int use_graph = 0;
   int sharded = 0;       // row-sharded multi-GPU mode (dist.cu)
   int lean = 0;          // loop body uses the flat 32-register passes
+  int owner_slot = -1;   // library context (host thread) that created the solver; solves must come from it
   int p2p = 0;           // row-sharded: exchanges go through peer memory inside the kernels, loop is a graph
   int include_P = 1;     // sharded: only rank 0 carries P + sigma I in the fused operator
   b200::PcgArgs* d_args = nullptr;
