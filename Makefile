@@ -16,7 +16,7 @@ LIBDIR  := osqp_b200/lib
 CSRC    := osqp_b200/csrc
 ARCH    := -gencode arch=compute_100a,code=sm_100a
 NVFLAGS := $(ARCH) -O3 -lineinfo --extended-lambda -std=c++17 -Xcompiler -fPIC -Iinclude -I$(CSRC) \
-           -diag-suppress 177
+           -diag-suppress 177 $(EXTRA)
 CFLAGS  := -O3 -fPIC -std=gnu11 -w -DNDEBUG
 CINC    := -Ialgebra/b200/config -Ialgebra/b200 -Iinclude \
            -I$(REF)/include/public -I$(REF)/include/private

@@ -941,7 +941,13 @@ def run_sharded(args):
                                "pass_A": {"bytes": ab, "us": phases["pass_A_us"], "gbs": ab / phases["pass_A_us"] / 1e3,
                                           "frac": ab / phases["pass_A_us"] / 1e3 / peak},
                                "phases_us": phases}
-        out["cpu_baseline"] = None
+        cpu = None
+        if world == 1 and not args.no_cpu_baseline:
+            try:        # N = 1 of the sharded arm: the oracle on a bounded sample of the same generator
+                cpu, out["parity"] = cpu_baseline_block(k, wl)
+            except Exception as exc:   # noqa: BLE001
+                cpu = {"value": None, "unit": "iter/s", "cores": 1, "kind": "reference", "sample": f"unavailable: {exc}"}
+        out["cpu_baseline"] = cpu
         args.emit(json.dumps(out))
     if dist is not None:
         dist.barrier()

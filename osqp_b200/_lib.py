@@ -12,7 +12,8 @@ import numpy as np
 from .interface import LoadedLibrary
 
 _HERE = Path(__file__).resolve().parent
-LIBDIR = _HERE / "lib"
+# B200_LIBDIR: development only -- a directory with alternative builds of BOTH libraries (make LIBDIR=...)
+LIBDIR = Path(os.environ["B200_LIBDIR"]).resolve() if os.environ.get("B200_LIBDIR") else _HERE / "lib"
 REPO_ROOT = _HERE.parent
 HEADER = REPO_ROOT / "include" / "osqp_b200.h"
 

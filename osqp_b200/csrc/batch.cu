@@ -29,6 +29,9 @@ using namespace b200;
 namespace {
 
 constexpr int kBB = 128;               // threads per CTA (= per QP)
+#ifndef B200_BATCH_MINBLOCKS
+#define B200_BATCH_MINBLOCKS 4         /* resident CTAs per SM the register allocation must allow (128 regs at 4) */
+#endif
 constexpr int kBW = kBB / 32;
 #ifdef B200_USE_FLOAT
 constexpr double kInfty = 1e17;        // OSQP_INFTY of a float build (osqp_api_constants.h:196-203)
@@ -93,7 +96,7 @@ __device__ __forceinline__ T row_dot(const int* __restrict__ rp, const int* __re
   return s;
 }
 
-__global__ void __launch_bounds__(kBB) batch_admm_kernel(BatchArgs a) {
+__global__ void __launch_bounds__(kBB, B200_BATCH_MINBLOCKS) batch_admm_kernel(BatchArgs a) {
   extern __shared__ __align__(16) unsigned char dsm_raw[];
   const int n = a.n, m = a.m, tid = threadIdx.x;
   T* base = reinterpret_cast<T*>(dsm_raw);
@@ -373,6 +376,9 @@ int b200_batch_solve(const b200_csr* P, const b200_csr* A, const b200_csr* At, i
   static thread_local size_t configured = 0;
   if (smem > configured) {
     if (!B200_CHECK(cudaFuncSetAttribute(batch_admm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem))) return 1;
+    // the iterates live in shared memory: give the kernel the whole carve-out (the default left 4 CTAs per SM)
+    B200_CHECK(cudaFuncSetAttribute(batch_admm_kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                    (int)cudaSharedmemCarveoutMaxShared));
     configured = smem;
   }
   int per_sm = 0;

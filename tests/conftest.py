@@ -17,6 +17,17 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
 
 
+def pytest_collection_modifyitems(config, items):
+    """`pytest tests` on a box without a GPU: the gpu-marked tests are skipped, not failed.  On a
+    box with a GPU nothing is skipped here: a library that does not come up there is a failure."""
+    if _gpu_visible():
+        return
+    skip = pytest.mark.skip(reason="no CUDA device on this box (gpu-marked test)")
+    for item in items:
+        if "gpu" in item.keywords:
+            item.add_marker(skip)
+
+
 def load_golden(name):
     """Golden fixture written by tests/golden/make_golden.py from the reference's own
     generate_problem.py scripts; sparse matrices are rebuilt as scipy CSC."""
@@ -62,11 +73,28 @@ def b200_lib():
     return load_library("f64")
 
 
+def _gpu_visible():
+    import shutil
+    if not shutil.which("nvidia-smi"):
+        return False
+    try:
+        out = subprocess.run(["nvidia-smi", "-L"], capture_output=True, text=True, timeout=30).stdout
+    except (OSError, subprocess.TimeoutExpired):
+        return False
+    return any(l.startswith("GPU ") for l in out.splitlines())
+
+
 @pytest.fixture(scope="session")
 def kern():
+    """The kernel library with a live context on cuda:0.  On a box WITHOUT a GPU the test is skipped
+    (`pytest tests` stays usable there); on a box WITH one, a failing b200_init is a hard failure --
+    there is no fallback to hide behind."""
     from osqp_b200.devmem import kernels
     k = kernels("f64")
-    assert k.b200_init(0) == 0, "b200_init failed: no usable GPU"
+    rc = k.b200_init(0)
+    if rc != 0 and not _gpu_visible():
+        pytest.skip("no CUDA device on this box")
+    assert rc == 0, "b200_init failed although a GPU is visible"
     yield k
     assert k.b200_last_error() == 0, "sticky CUDA error recorded during the session"
 

@@ -108,3 +108,24 @@ def test_batch_larger_than_one_wave(b200_lib):
         s.cleanup()
         assert abs(rb.obj_val[i] - r.info.obj_val) <= 5e-3 * max(1.0, abs(r.info.obj_val))
     tmpl.cleanup()
+
+
+def test_batch_float32_build(b200_lib):
+    """the f32 build of the batched kernel (the reference CUDA backend's default precision): every QP solved,
+    objectives within 1e-3 of the f64 batch at eps 1e-3"""
+    from osqp_b200._lib import lib_paths
+    if not lib_paths("f32")[1].exists():
+        pytest.skip("f32 library not built")
+    nb = 32
+    base, L, U = mpc_batch(nb, seed=21)
+    st = dict(BENCH, check_dualgap=0)        # the gap of an f32 iterate sits at its rounding level
+    t64 = OSQP("f64").setup(base["P"], base["q"], base["A"], base["l"], base["u"], **st)
+    r64 = t64.solve_batch(L, U)
+    t64.cleanup()
+    t32 = OSQP("f32").setup(base["P"], base["q"], base["A"], base["l"], base["u"], **st)
+    r32 = t32.solve_batch(L, U)
+    t32.cleanup()
+    assert (r64.status_val == _capi.OSQP_SOLVED).all() and (r32.status_val == _capi.OSQP_SOLVED).all()
+    assert np.abs(r32.obj_val - r64.obj_val).max() <= 5e-3 * np.maximum(1.0, np.abs(r64.obj_val)).max()
+    Ax = r32.x.astype(np.float64) @ base["A"].T.toarray()
+    assert np.maximum(np.maximum(L - Ax, Ax - U), 0).max() <= 5e-3 * (1 + np.abs(Ax).max())
