@@ -376,9 +376,9 @@ int b200_batch_solve(const b200_csr* P, const b200_csr* A, const b200_csr* At, i
   static thread_local size_t configured = 0;
   if (smem > configured) {
     if (!B200_CHECK(cudaFuncSetAttribute(batch_admm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem))) return 1;
-    // the iterates live in shared memory: give the kernel the whole carve-out (the default left 4 CTAs per SM)
-    B200_CHECK(cudaFuncSetAttribute(batch_admm_kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
-                                    (int)cudaSharedmemCarveoutMaxShared));
+    // NOT the maximum shared-memory carve-out: 5-6 CTAs per SM then fit, but L1 shrinks below the 30 KB of
+    // matrix entries every CTA re-reads through the read-only path -- measured 46 ms (4 CTAs), 45 ms (5),
+    // 43 ms (6) against 31 ms with the default carve-out and 4 CTAs per SM (gpurun_out/r2c15_batch_variants.log)
     configured = smem;
   }
   int per_sm = 0;
