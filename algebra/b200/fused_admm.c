@@ -28,9 +28,7 @@ void osqp_ref_update_z(OSQPSolver* solver);
 void osqp_ref_update_y(OSQPSolver* solver);
 void osqp_ref_update_info(OSQPSolver* solver, OSQPInt iter, OSQPInt polishing);
 OSQPInt osqp_ref_check_termination(OSQPSolver* solver, OSQPInt approximate);
-/* non-static in the unmodified auxil.c (src/auxil.c:460,520), not declared in auxil.h */
-OSQPInt is_primal_infeasible(OSQPSolver* solver, OSQPFloat eps_prim_inf);
-OSQPInt is_dual_infeasible(OSQPSolver* solver, OSQPFloat eps_dual_inf);
+
 
 /* A x carried through the relaxation step: valid from the first exact product of a
  * solve (update_info at iteration 1) until the solve ends; recomputed exactly every
@@ -215,8 +213,8 @@ void update_info(OSQPSolver* solver, OSQPInt iter, OSQPInt polishing) {
  * (auxil.c:460-585) each start with two or three blocking reductions whose values alone decide
  * whether the test can return non-zero at all: ||delta_y|| > tol and u'dy+ + l'dy- < 0, resp.
  * ||delta_x|| > tol and q'dx < 0.  Those five scalars come from ONE kernel
- * (b200_admm_infeas_scalars); only when they leave the outcome open is the reference function
- * itself called -- it recomputes the same quantities and goes on to the matrix products. */
+ * (b200_admm_infeas_scalars); only when they leave the outcome open do the matrix products of the
+ * tests follow, with the same calls as the reference minus the reductions already in hand. */
 OSQPInt check_termination(OSQPSolver* solver, OSQPInt approximate) {
   OSQPInfo*      info     = solver->info;
   OSQPSettings*  settings = solver->settings;
@@ -272,7 +270,8 @@ OSQPInt check_termination(OSQPSolver* solver, OSQPInt approximate) {
   if (info->dual_res < eps_dual) dual_ok = 1;
   else need_d = 1;
 
-  /* infeasibility tests: pre-test from one kernel, the reference function only when it can fire */
+  /* infeasibility tests: the reductions they start with from one kernel, the matrix products only when
+     those leave the outcome open */
   if (need_p || need_d) {
     /* writes delta_y only: the norms parked by update_info stay valid for compute_rho_estimate */
     int live = b200_norm_cache_live();
@@ -282,10 +281,27 @@ OSQPInt check_termination(OSQPSolver* solver, OSQPInt approximate) {
                              OSQP_INFTY * OSQP_MIN_SCALING, (int)work->data->n, (int)work->data->m,
                              need_p, need_d, f);
     b200_norm_cache_after(live, work->delta_y->d_val, work->delta_y->length);
-    if (need_p && f[0] > OSQP_DIVISION_TOL && (f[1] + f[2]) < 0.0)
-      prim_inf = is_primal_infeasible(solver, eps_prim_inf);
-    if (need_d && f[3] > OSQP_DIVISION_TOL && f[4] < 0.0)
-      dual_inf = is_dual_infeasible(solver, eps_dual_inf);
+    /* is_primal_infeasible (auxil.c:460-514) from here on: ||A' dy|| < eps ||dy||, with the unscaling
+       folded into the norm (max |Dinv_i v_i| is what ew_prod + norm_inf compute, product by product) */
+    if (need_p && f[0] > OSQP_DIVISION_TOL && (f[1] + f[2]) < 0.0) {
+      OSQPMatrix_Atxpy(work->data->A, work->delta_y, work->Atdelta_y, 1.0, 0.0);
+      tmp = unscale ? OSQPVectorf_scaled_norm_inf(work->scaling->Dinv, work->Atdelta_y)
+                    : OSQPVectorf_norm_inf(work->Atdelta_y);
+      prim_inf = tmp < eps_prim_inf * (OSQPFloat)f[0];
+    }
+    /* is_dual_infeasible (auxil.c:516-585): ||P dx|| < c eps ||dx||, then A dx in the recession cone */
+    if (need_d && f[3] > OSQP_DIVISION_TOL && f[4] < 0.0) {
+      OSQPFloat cost_scaling = unscale ? work->scaling->c : 1.0;
+      OSQPMatrix_Axpy(work->data->P, work->delta_x, work->Pdelta_x, 1.0, 0.0);
+      tmp = unscale ? OSQPVectorf_scaled_norm_inf(work->scaling->Dinv, work->Pdelta_x)
+                    : OSQPVectorf_norm_inf(work->Pdelta_x);
+      if (tmp < cost_scaling * eps_dual_inf * (OSQPFloat)f[3]) {
+        OSQPMatrix_Axpy(work->data->A, work->delta_x, work->Adelta_x, 1.0, 0.0);
+        if (unscale) OSQPVectorf_ew_prod(work->Adelta_x, work->Adelta_x, work->scaling->Einv);
+        dual_inf = OSQPVectorf_in_reccone(work->Adelta_x, work->data->l, work->data->u,
+                                          OSQP_INFTY * OSQP_MIN_SCALING, eps_dual_inf * (OSQPFloat)f[3]);
+      }
+    }
   }
 
   /* duality gap (compute_duality_gap_tol) */
