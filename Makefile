@@ -40,11 +40,12 @@ $(LIBDIR)/libb200_kernels_f32.so: $(CU_SRC) $(CU_HDR)
 	@mkdir -p $(LIBDIR)
 	$(NVCC) $(NVFLAGS) -DB200_USE_FLOAT -shared -o $@ $(CU_SRC) -cudart static -ldl
 
-# auxil.c is compiled from the reference tree UNCHANGED, with six of its functions renamed on the
+# auxil.c is compiled from the reference tree UNCHANGED, with seven of its functions renamed on the
 # command line so that algebra/b200/fused_admm.c can provide the fused versions (see that file)
 FUSE_RENAMES := -Dupdate_xz_tilde=osqp_ref_update_xz_tilde -Dupdate_x=osqp_ref_update_x \
                 -Dupdate_z=osqp_ref_update_z -Dupdate_y=osqp_ref_update_y \
-                -Dupdate_info=osqp_ref_update_info -Dcheck_termination=osqp_ref_check_termination
+                -Dupdate_info=osqp_ref_update_info -Dcheck_termination=osqp_ref_check_termination \
+                -Dstore_solution=osqp_ref_store_solution
 CORE_REST    := $(filter-out $(REF)/src/auxil.c,$(CORE_SRC))
 
 $(LIBDIR)/auxil_f64.o: $(REF)/src/auxil.c Makefile

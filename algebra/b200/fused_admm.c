@@ -8,6 +8,7 @@
  *     -Dupdate_z=osqp_ref_update_z -Dupdate_y=osqp_ref_update_y -Dupdate_info=osqp_ref_update_info
  *     -Dcheck_termination=osqp_ref_check_termination   (the macro also renames the OSQPSettings field of
  *      that name inside this one translation unit -- consistently, so the layout is untouched)
+ *     -Dstore_solution=osqp_ref_store_solution
  * so that the reference definitions keep existing under the osqp_ref_ names (and can be selected
  * at run time with OSQP_B200_UNFUSED=1 for A/B parity runs), while the calls made by
  * src/osqp_api.c:708-726 bind to the versions below.  Expression order follows the reference's
@@ -19,6 +20,7 @@
 #include "algebra_impl.h"
 #include "timing.h"
 #include "glob_opts.h"
+#include "scaling.h"
 
 #include <stdlib.h>
 
@@ -28,6 +30,7 @@ void osqp_ref_update_z(OSQPSolver* solver);
 void osqp_ref_update_y(OSQPSolver* solver);
 void osqp_ref_update_info(OSQPSolver* solver, OSQPInt iter, OSQPInt polishing);
 OSQPInt osqp_ref_check_termination(OSQPSolver* solver, OSQPInt approximate);
+void osqp_ref_store_solution(OSQPSolver* solver, OSQPSolution* solution);
 
 
 /* A x carried through the relaxation step: valid from the first exact product of a
@@ -332,4 +335,46 @@ OSQPInt check_termination(OSQPSolver* solver, OSQPInt approximate) {
     exitflag      = 1;
   }
   return exitflag;
+}
+
+
+/* store_solution (auxil.c:598-675).  For a run that ended with a solution the reference fills two device
+ * vectors with NaN and downloads them into the certificate arrays: (n + m) values over PCIe per solve --
+ * 240 MB on BASELINE configs[3], 20-40 ms of a 330 ms solve.  The host arrays are filled with NaN here
+ * directly, and not at all when they still hold the NaN of the previous call (first and last entry are
+ * looked at: the arrays only ever hold all-OSQP_NAN, a certificate normalised to |v| <= 1, or the zeros of a fresh
+ * allocation).  The device vectors are still set to NaN, as the reference leaves them.  Every other case
+ * (no solution: NaN iterates, certificates; a caller-provided OSQPSolution) goes through the reference
+ * function. */
+static int all_nan_already(const OSQPFloat* a, OSQPInt len) {
+  /* OSQP_NAN is the finite marker value (OSQPFloat)0x7fc00000; a normalised certificate never holds it */
+  return len == 0 || (a[0] == OSQP_NAN && a[len - 1] == OSQP_NAN);
+}
+
+void store_solution(OSQPSolver* solver, OSQPSolution* solution) {
+  OSQPWorkspace* work = solver->work;
+  OSQPInt i, n, m;
+  if (!solution) return;
+  /* only the solver's own (host, calloc'ed by osqp_setup) solution arrays are written from the host; the
+     arrays osqp_get_solution is handed may live in device memory (tests/basic_qp/test_cuda_io.cpp) */
+  if (unfused() || solution != solver->solution || !has_solution(solver->info)) {
+    osqp_ref_store_solution(solver, solution);
+    return;
+  }
+  if (solver->settings->scaling) {
+    unscale_solution(work->x_prev, work->z_prev, work->x, work->y, work);
+    OSQPVectorf_to_raw(solution->x, work->x_prev);
+    OSQPVectorf_to_raw(solution->y, work->z_prev);
+  } else {
+    OSQPVectorf_to_raw(solution->x, work->x);
+    OSQPVectorf_to_raw(solution->y, work->y);
+  }
+  OSQPVectorf_set_scalar(work->delta_y, OSQP_NAN);
+  OSQPVectorf_set_scalar(work->delta_x, OSQP_NAN);
+  n = work->delta_x->length;
+  m = work->delta_y->length;
+  if (!all_nan_already(solution->prim_inf_cert, m))
+    for (i = 0; i < m; i++) solution->prim_inf_cert[i] = OSQP_NAN;
+  if (!all_nan_already(solution->dual_inf_cert, n))
+    for (i = 0; i < n; i++) solution->dual_inf_cert[i] = OSQP_NAN;
 }

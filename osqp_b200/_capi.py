@@ -30,6 +30,7 @@ OSQP_NON_CVX = 9
 OSQP_SIGINT = 10
 OSQP_UNSOLVED = 11
 OSQP_INFTY = 1e30  # osqp_api_constants.h:196-203 (non CUDA+float value)
+OSQP_NAN = float(0x7fc00000)  # osqp_api_constants.h:192-194: a finite marker value, not an IEEE NaN
 
 
 def make_types(c_float):

@@ -159,11 +159,18 @@ class OSQP:
                 return np.zeros(0, dtype=dt)
             return np.ctypeslib.as_array(ptr, shape=(n,)).astype(dt, copy=True)
 
+        def cert(ptr, n):
+            # store_solution (auxil.c:627-631) fills a certificate that does not apply with OSQP_NAN: copying
+            # (n + m) marker values per solve costs as much as copying the solution itself -- None instead
+            if n == 0 or not ptr or (ptr[0] == _capi.OSQP_NAN and ptr[n - 1] == _capi.OSQP_NAN):
+                return None
+            return arr(ptr, n)
+
         inf = SimpleNamespace(**{k: getattr(info, k) for k, _ in info._fields_})
         inf.status = info.status.decode()
         return SimpleNamespace(x=arr(sol.x, self.n), y=arr(sol.y, self.m),
-                               prim_inf_cert=arr(sol.prim_inf_cert, self.m),
-                               dual_inf_cert=arr(sol.dual_inf_cert, self.n),
+                               prim_inf_cert=cert(sol.prim_inf_cert, self.m),
+                               dual_inf_cert=cert(sol.dual_inf_cert, self.n),
                                info=inf)
 
     def update(self, q=None, l=None, u=None, Px=None, Px_idx=None, Ax=None, Ax_idx=None):

@@ -76,6 +76,41 @@ def test_primal_infeasible_random_problem(b200_lib):
     assert abs(np.abs(r.prim_inf_cert).max() - 1.0) < 1e-9       # normalised certificate
 
 
+def test_certificate_arrays_after_infeasible_then_feasible(b200_lib):
+    """store_solution (auxil.c:598-675) through the backend's fused version: a run with a solution leaves
+    OSQP_NAN in both certificate arrays -- also when the previous run of the same solver wrote a
+    certificate there -- and an infeasible run writes the normalised certificate over the OSQP_NAN."""
+    P = sp.csc_matrix(np.diag([1.0, 2.0, 0.5]))
+    q = np.array([1.0, -1.0, 0.5])
+    A = sp.csc_matrix(np.array([[1.0, 1.0, 0.0], [1.0, 1.0, 0.0], [0.0, 0.0, 1.0]]))
+    l_bad, u_bad = np.array([1.0, -np.inf, -1.0]), np.array([np.inf, 0.0, 1.0])      # x0 + x1 >= 1 and <= 0
+    l_ok, u_ok = np.array([-1.0, -np.inf, -1.0]), np.array([np.inf, 2.0, 1.0])
+    st = dict(FIXTURE_SETTINGS)
+    st.update(warm_starting=0, polishing=0)
+    s = OSQP(b200_lib).setup(P, q, A, l_ok, u_ok, **st)
+    sol = s._solver.contents.solution.contents
+    nan = _capi.OSQP_NAN
+
+    def raw(ptr, k):
+        return np.array([ptr[i] for i in range(k)])
+
+    r = s.solve()
+    assert r.info.status_val == _capi.OSQP_SOLVED and r.prim_inf_cert is None and r.dual_inf_cert is None
+    assert (raw(sol.prim_inf_cert, 3) == nan).all() and (raw(sol.dual_inf_cert, 3) == nan).all()
+    x_ok = r.x.copy()
+    s.update(l=l_bad, u=u_bad)
+    r = s.solve()
+    assert r.info.status_val == _capi.OSQP_PRIMAL_INFEASIBLE
+    assert r.dual_inf_cert is None and abs(np.abs(r.prim_inf_cert).max() - 1.0) < 1e-9
+    assert (raw(sol.dual_inf_cert, 3) == nan).all()
+    s.update(l=l_ok, u=u_ok)
+    r = s.solve()
+    assert r.info.status_val == _capi.OSQP_SOLVED and r.prim_inf_cert is None
+    assert (raw(sol.prim_inf_cert, 3) == nan).all() and (raw(sol.dual_inf_cert, 3) == nan).all()
+    assert np.allclose(r.x, x_ok, atol=1e-3)
+    s.cleanup()
+
+
 @pytest.mark.parametrize("A,u,status", [
     ("A12", "u1", _capi.OSQP_SOLVED), ("A12", "u2", _capi.OSQP_PRIMAL_INFEASIBLE),
     ("A34", "u3", _capi.OSQP_DUAL_INFEASIBLE), ("A34", "u4", _capi.OSQP_PRIMAL_INFEASIBLE)])

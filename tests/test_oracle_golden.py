@@ -68,6 +68,9 @@ def test_primal_infeasibility(oracle_lib):
     d = load_golden("primal_infeasibility")
     s, r = solve(oracle_lib, d, polishing=1, scaling=0, warm_starting=0)
     assert r.info.status_val == _capi.OSQP_PRIMAL_INFEASIBLE
+    # the wrapper hands out a certificate only where the core wrote one (OSQP_NAN marker elsewhere)
+    assert r.dual_inf_cert is None and abs(np.abs(r.prim_inf_cert).max() - 1.0) < 1e-9
+    assert (r.x == _capi.OSQP_NAN).all()
 
 
 @pytest.mark.parametrize("A,u,status", [
