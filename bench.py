@@ -632,7 +632,8 @@ def run_single(args):
                                                 iters / args.steps)
             if not args.no_same_config:
                 try:
-                    # the full-size oracle solve gets what is left of a 5-minute bench
+                    # the full-size oracle solve (started in the background at t_start) gets what is left of the budget,
+                    # so the whole default run stays near 2.5 minutes
                     out["cpu_baseline_same_config"] = same_config_block(
                         k, oracle_full, args.same_config_budget - (time.perf_counter() - t_start))
                 except Exception as exc:   # noqa: BLE001
@@ -987,7 +988,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true", help="skip cpu_baseline / parity / ref_cuda / same-config blocks")
     ap.add_argument("--no-ref-cuda", action="store_true")
     ap.add_argument("--no-same-config", action="store_true")
-    ap.add_argument("--same-config-budget", type=float, default=300.0,
+    ap.add_argument("--same-config-budget", type=float, default=150.0,
                     help="seconds after which the full-size oracle solve of configs[0] is abandoned")
     ap.add_argument("--no-strong-baseline", action="store_true")
     ap.add_argument("--sharded-e2e-steps", type=int, default=5)
